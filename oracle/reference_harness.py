@@ -1,0 +1,118 @@
+"""Import and drive the UNMODIFIED reference (hynekdav/semi-supervised-VOS) on CPU.
+
+TEST INFRASTRUCTURE ONLY (see oracle/propagation_oracle.py).  Used by ``oracle/make_golden.py``
+(build container, where ``/root/reference`` exists) and by ``bench.py --impl reference`` when a
+copy of the reference is present (``/root/reference`` or ``baseline/_ref``).  Nothing here is
+on the product path.
+
+The reference needs three compatibility shims on a modern stack; they
+are applied to the *environment*, never to the reference's sources:
+  1. ``numpy.int``            (src/model/predict.py:85, src/utils/datasets.py:145)
+  2. ``PIL.Image.ANTIALIAS``  (src/utils/datasets.py:146)
+  3. ``model_zoo.load_url``   (src/model/backbone/resnet.py:194 -- pretrained download, no network)
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+from pathlib import Path
+from typing import Optional
+
+REPO = Path(__file__).resolve().parent.parent
+CANDIDATES = [Path('/root/reference'), REPO / 'baseline' / '_ref']
+
+
+def find_reference() -> Optional[Path]:
+    for c in CANDIDATES:
+        if (c / 'src' / 'model' / 'predict.py').is_file():
+            return c
+    return None
+
+
+def import_reference(device: str = 'cpu'):
+    """Returns a namespace with the reference modules; raises if the reference is absent."""
+    root = find_reference()
+    if root is None:
+        raise FileNotFoundError('reference sources not found in ' + ', '.join(map(str, CANDIDATES)))
+    import numpy as np
+    import PIL.Image
+    if not hasattr(np, 'int'):
+        np.int = int  # shim 1
+    if not hasattr(PIL.Image, 'ANTIALIAS'):
+        PIL.Image.ANTIALIAS = PIL.Image.LANCZOS  # shim 2
+    for name in list(sys.modules):
+        if name == 'src' or name.startswith('src.'):
+            raise RuntimeError(f'a different `src` package ({name}) is already imported; run the '
+                               'reference in its own process')
+    sys.path.insert(0, str(root))
+    try:
+        import torch
+        resnet = importlib.import_module('src.model.backbone.resnet')
+        resnet.model_zoo.load_url = lambda url, *a, **k: {}  # shim 3
+        ns = type('Reference', (), {})()
+        ns.root = root
+        ns.config = importlib.import_module('src.config')
+        ns.config.Config.DEVICE = torch.device(device)
+        ns.predict = importlib.import_module('src.model.predict')
+        ns.utils = importlib.import_module('src.utils.utils')
+        ns.inference_utils = importlib.import_module('src.utils.inference_utils')
+        ns.vos_net = importlib.import_module('src.model.vos_net')
+        ns.resnet = resnet
+    finally:
+        sys.path.remove(str(root))
+    return ns
+
+
+def run_inference_single(ref, features, first_label_full, palette, workdir, video='clip',
+                         sigma_1=8.0, sigma_2=21.0, frame_range=40, ref_num=9, temperature=1.0,
+                         probability_propagation=False):
+    """Drive the reference's REAL ``inference_single`` (src/utils/inference_utils.py:23-87) with a
+    table-lookup 'model' (features precomputed) and record every ``predict`` result.
+
+    Returns (masks (T-1,H,W) uint8 read back from the PNGs it wrote, list of (d,P) predictions).
+    """
+    import numpy as np
+    import torch
+    from PIL import Image
+
+    T = features.shape[0]
+    H, W = first_label_full.shape
+    workdir = Path(workdir)
+    ann_dir = workdir / 'Annotations' / '480p'
+    (ann_dir / video).mkdir(parents=True, exist_ok=True)
+    img = Image.fromarray(first_label_full.astype(np.uint8), mode='P')
+    img.putpalette(palette)
+    img.save(ann_dir / video / '00000.png')
+    save = workdir / 'out'
+
+    class TableModel:
+        def __call__(self, inp):
+            return features[int(inp[0, 0, 0, 0].item())][None]
+
+    loader = [(torch.full((1, 1, H, W), float(t)), (video,)) for t in range(T)]
+    recorded = []
+    iu = ref.inference_utils
+    real_predict = ref.predict.predict
+
+    def recording_predict(*a, **k):
+        out = real_predict(*a, **k)
+        recorded.append(out.clone())
+        return out
+
+    iu.predict = recording_predict
+    try:
+        with torch.no_grad():
+            iu.inference_single(TableModel(), loader, T, ann_dir, video, str(save), sigma_1,
+                                sigma_2, frame_range, ref_num, temperature,
+                                probability_propagation, True)
+    finally:
+        iu.predict = real_predict
+    masks = np.stack([np.asarray(Image.open(save / video / f'{t:05d}.png')) for t in range(1, T)])
+    return masks.astype(np.uint8), recorded
+
+
+def default_palette():
+    pal = [0, 0, 0, 128, 0, 0, 0, 128, 0, 128, 128, 0, 0, 0, 128, 128, 0, 128, 0, 128, 128,
+           128, 128, 128, 64, 0, 0, 192, 0, 0, 64, 128, 0, 192, 128, 0]
+    return pal + [0] * (768 - len(pal))

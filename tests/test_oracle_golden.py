@@ -1,0 +1,104 @@
+"""Pins the CPU oracle (oracle/propagation_oracle.py) to outputs of the REAL reference
+(tests/golden, produced by oracle/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import propagation_oracle as O
+from tests import _golden as G
+
+
+def test_sample_frames_table():
+    table = np.load(G.GOLDEN / 'sample_frames.npz')['table']
+    assert len(table) > 2000
+    for row in table:
+        ref_num, rng, t, n = (int(v) for v in row[:4])
+        assert O.sample_frames(t, rng, ref_num) == row[4:4 + n].tolist(), (ref_num, rng, t)
+
+
+def test_sample_frames_small_ref_num_raises_like_reference():
+    # negative sparse_num -> np.linspace ValueError in the reference
+    with pytest.raises(ValueError):
+        O.sample_frames(5, 40, 2)
+    assert O.sample_frames(2, 40, 2) == [0, 1]
+
+
+def test_max_lookback_bounds_ring():
+    for ref_num in (3, 4, 9, 20):
+        for rng in (6, 10, 40):
+            for t in range(1, 300):
+                assert t - min(O.sample_frames(t, rng, ref_num)) <= max(O.max_lookback(rng), ref_num)
+
+
+def test_spatial_weight_bit_exact():
+    z = np.load(G.GOLDEN / 'spatial_weight.npz')
+    for key in z.files:
+        _, h, w, s = key.split('_')
+        got = O.spatial_weight((int(h), int(w)), float(s)).numpy()
+        assert np.array_equal(got, z[key]), key
+        cols = slice(3, 17)
+        assert np.array_equal(O.spatial_weight((int(h), int(w)), float(s), cols).numpy(), z[key][:, cols])
+
+
+def test_first_frame_labels_bit_exact():
+    z = np.load(G.GOLDEN / 'first_frame_labels.npz')
+    for key in z.files:
+        if not key.startswith('first_'):
+            continue
+        low, d = O.first_frame_labels(z[key])
+        assert d == int(z[key].max()) + 1
+        assert np.array_equal(low.numpy().astype(np.uint8), z['low_' + key[6:]]), key
+
+
+def test_predict_cases():
+    feats, hist, prob_hist = G.predict_case_inputs()
+    z = np.load(G.GOLDEN / 'predict_cases.npz')
+    for key in z.files:
+        c = G.parse_case(key)
+        lab = (prob_hist if c['prob'] else hist)[:, :c['t']]
+        for chunk in (None, 50):
+            got = O.predict(feats[:c['t']], feats[c['t']], lab, 8.0, 21.0, c['t'], c['frame_range'],
+                            c['ref_num'], c['temperature'], c['prob'], chunk=chunk).numpy()
+            # un-chunked follows the reference op for op (bit-exact); chunked differs by GEMM blocking
+            if chunk is None:
+                assert np.array_equal(got, z[key]), key
+            else:
+                np.testing.assert_allclose(got, z[key], rtol=0, atol=2e-6, err_msg=key)
+
+
+@pytest.mark.parametrize('name', G.SEQ_NAMES)
+def test_sequences_match_reference_inference_single(name):
+    feats, first, run = G.sequence_inputs(name)
+    masks_ref, preds_ref = G.sequence_golden(name)
+    masks, preds = O.propagate_sequence(feats, first, **run)
+    assert np.array_equal(masks.numpy().astype(np.uint8), masks_ref)
+    assert np.array_equal(torch.stack(preds).numpy(), preds_ref)
+
+
+def test_topk_extension_reduces_to_reference_when_k_covers_everything():
+    feats, hist, _ = G.predict_case_inputs()
+    t = 10
+    N = t * feats.shape[2] * feats.shape[3]
+    full = O.predict(feats[:t], feats[t], hist[:, :t], 8.0, 21.0, t, 40, 9, 1.0, False)
+    big = O.predict(feats[:t], feats[t], hist[:, :t], 8.0, 21.0, t, 40, 9, 1.0, False, topk=N)
+    assert torch.equal(full, big)
+    k5, idx = O.predict(feats[:t], feats[t], hist[:, :t], 8.0, 21.0, t, 40, 9, 1.0, False, topk=5,
+                        return_topk_idx=True)
+    assert idx.shape == (feats.shape[2] * feats.shape[3], 5)
+    assert not torch.equal(full, k5)
+
+
+def test_upsample_commutes_with_argmax():
+    g = torch.Generator().manual_seed(1)
+    for (H, W) in ((96, 160), (100, 150), (61, 83)):
+        H_d, W_d = O.lowres_dims(H, W)
+        pred = torch.rand(4, H_d * W_d, generator=g)
+        up = torch.nn.functional.interpolate(pred.view(1, 4, H_d, W_d), size=(H, W), mode='nearest')
+        assert torch.equal(torch.argmax(up, 1)[0], O.upsample_mask(pred.argmax(0), H_d, W_d, H, W))
+
+
+def test_ref_sigmas_matches_slice_semantics():
+    assert O.ref_sigmas(10, 9, 8.0, 21.0) == [8.0] * 9
+    assert O.ref_sigmas(16, 9, 8.0, 21.0) == [21.0] * 5 + [8.0] * 4
+    assert O.ref_sigmas(20, 3, 8.0, 21.0) == [8.0] * 3
+    assert O.ref_sigmas(20, 4, 8.0, 21.0) == [8.0] * 4
