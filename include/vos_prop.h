@@ -1,0 +1,124 @@
+/* vos_prop.h -- C ABI of the B200 label-propagation engine (libvosprop.so).
+ *
+ * Drop-in scope: the transductive label-propagation hot path of hynekdav/semi-supervised-VOS.
+ * The reference has no FFI; its boundary is a set of Python callables.
+ * Each entry point below replaces one of them (reference file:line in the comment).  The Python
+ * mirror under semi-supervised-vos_b200/src/ binds these with ctypes.
+ *
+ * Conventions: plain C, raw device pointers, cudaStream_t passed as void*, every call is
+ * stream-ordered and never synchronises the device; int return (0 = ok, <0 = error, message via
+ * vosprop_last_error()); no exceptions cross the ABI; a handle is not thread-safe.
+ * There is NO CPU fallback: on a machine without an sm_100 device vosprop_create() fails.
+ */
+#ifndef VOS_PROP_H_
+#define VOS_PROP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VOSPROP_ABI_VERSION 1
+#define VOSPROP_MAX_REFS 32     /* reference frames per step (reference default ref_num = 9)   */
+#define VOSPROP_MAX_CLASSES 14  /* d = objects + 1 (DAVIS <= 11, YouTube-VOS <= 11)            */
+#define VOSPROP_FEAT_DIM 256    /* VOSNet embedding width, src/model/vos_net.py:22             */
+#define VOSPROP_TILE 128        /* pixel tile of the affinity kernel                           */
+
+enum vosprop_status {
+    VOSPROP_OK = 0,
+    VOSPROP_ERR_INVALID = -1,   /* bad argument                                                */
+    VOSPROP_ERR_CUDA = -2,      /* CUDA runtime / driver error (string has the detail)         */
+    VOSPROP_ERR_UNSUPPORTED = -3, /* no sm_100 device / shape beyond engine capacity           */
+    VOSPROP_ERR_STATE = -4      /* call order violated (e.g. reference frame not in the ring)  */
+};
+
+enum vosprop_dtype { VOSPROP_F32 = 0, VOSPROP_F16 = 1, VOSPROP_BF16 = 2 };
+/* memory order of a feature map handed to vosprop_append_features */
+enum vosprop_layout { VOSPROP_NCHW = 0 /* (K, H_d*W_d), torch default */, VOSPROP_NHWC = 1 /* (H_d*W_d, K) */ };
+enum vosprop_kernel {
+    VOSPROP_KERNEL_TC = 0,   /* product path: TMA + tcgen05 bf16x3 fused affinity kernel        */
+    VOSPROP_KERNEL_SIMT = 1  /* on-device fp32 checker (CUDA cores), same data path; tests only */
+};
+
+typedef struct vosprop_engine vosprop_engine;
+
+typedef struct vosprop_config {
+    int32_t device;         /* CUDA ordinal                                                     */
+    int32_t max_pixels;     /* largest H_d*W_d this engine will see (480p: 6420, 1080p: 32400)  */
+    int32_t ring_slots;     /* reference-memory ring size; >= frame_range + 4 + 1 (44+1)        */
+    int32_t max_fullres_pixels; /* largest H*W (for the full-resolution mask staging buffer)    */
+} vosprop_config;
+
+/* One propagation step == one call of the reference's predict() (src/model/predict.py:19-71)
+ * plus the label / mask write-back of inference_single (src/utils/inference_utils.py:67-75). */
+typedef struct vosprop_step {
+    int32_t frame_idx;                       /* target frame; its features must be in the ring  */
+    int32_t n_refs;                          /* number of reference frames                      */
+    int32_t ref_frames[VOSPROP_MAX_REFS];    /* frame indices (duplicates allowed, as index_select) */
+    float ref_sigma[VOSPROP_MAX_REFS];       /* Gaussian prior sigma per ref; <= 0: no prior    */
+    float temperature;                       /* multiplies the logits (predict.py:52); >= 0     */
+    int32_t probability_propagation;         /* 1: store raw prediction as the new label (inference_utils.py:67-68) */
+    int32_t write_labels;                    /* 1: write the new label into the ring (normal); 0: pure predict()  */
+    int32_t topk;                            /* 0: full softmax (reference); >0: top-k extension */
+    int32_t kernel;                          /* enum vosprop_kernel                             */
+    float* out_prediction;                   /* device (d, P) fp32 or NULL  -- predict()'s return value */
+    uint8_t* out_mask_lowres;                /* device (P) uint8 or NULL    -- argmax over d at stride 8 */
+    uint8_t* out_mask_fullres;               /* device (H, W) uint8 or NULL -- nearest up-sample + argmax (inference_utils.py:74-75) */
+    int32_t* out_topk_idx;                   /* device (P, topk) int32 or NULL (top-k mode only) */
+} vosprop_step;
+
+const char* vosprop_last_error(void);
+int vosprop_abi_version(void);
+
+/* Engine lifetime (one per sequence in flight; owns ring buffer, TMA descriptors, scratch). */
+int vosprop_create(const vosprop_config* cfg, vosprop_engine** out);
+void vosprop_destroy(vosprop_engine* e);
+
+/* New video: geometry + class count.  Replaces the state reset at a video boundary
+ * (src/utils/inference_utils.py:28-48) and the prior set-up of prepare_first_frame
+ * (src/model/predict.py:117-118: the (P,P) Gaussian matrices are never built; the kernel
+ * evaluates the closed form).  H_d, W_d: feature-map size; H, W: full frame size; d: classes. */
+int vosprop_reset(vosprop_engine* e, int32_t H_d, int32_t W_d, int32_t H, int32_t W, int32_t d, void* stream);
+
+/* Append frame `frame_idx`'s embedding to the ring (slot = frame_idx % ring_slots).  Replaces
+ * `feats_history = torch.cat(...)` (inference_utils.py:72, :36).  `features`: device pointer to
+ * K x P (NCHW) or P x K (NHWC) elements of `dtype`. */
+int vosprop_append_features(vosprop_engine* e, int32_t frame_idx, const void* features,
+                            int32_t dtype, int32_t layout, void* stream);
+
+/* Set frame `frame_idx`'s labels from a class-index map (device, P x uint8): the one-hot first
+ * frame of get_labels (predict.py:92-96).  */
+int vosprop_set_labels_index(vosprop_engine* e, int32_t frame_idx, const uint8_t* class_idx, void* stream);
+/* Set frame `frame_idx`'s labels from a (d, P) fp32 device array (probability propagation or an
+ * externally supplied history, label_history[:, t]). */
+int vosprop_set_labels_dense(vosprop_engine* e, int32_t frame_idx, const float* labels, void* stream);
+
+/* The hot path: fused affinity + softmax + prior + label gather, then merge / argmax /
+ * ring-buffer label update / mask write-back.  3 kernel launches, no host sync. */
+int vosprop_propagate(vosprop_engine* e, const vosprop_step* step, void* stream);
+
+/* sample_frames (src/model/predict.py:74-89), host only.  Writes up to VOSPROP_MAX_REFS indices,
+ * returns the count, or VOSPROP_ERR_INVALID where the reference raises (num_refs < 3 once
+ * frame_idx > num_refs -> negative linspace count). */
+int vosprop_sample_frames(int32_t frame_idx, int32_t take_range, int32_t num_refs, int32_t* out_idx);
+
+/* Convenience: sample_frames + the sigma-per-ref rule of predict.py:60-66, filled into `step`
+ * (frame_idx, n_refs, ref_frames, ref_sigma).  sigma <= 0 disables the prior (probability mode). */
+int vosprop_plan_step(int32_t frame_idx, int32_t take_range, int32_t num_refs, float sigma_dense,
+                      float sigma_sparse, int32_t probability_propagation, vosprop_step* step);
+
+/* Introspection for tests / bench. */
+int vosprop_ring_slots(const vosprop_engine* e);
+int vosprop_num_sms(const vosprop_engine* e);
+/* Work decomposition of the affinity kernel (host arithmetic shared with the device code):
+ * fills grid size and per-CTA [begin,end) of the linearised (m_tile, n_tile) space. */
+int vosprop_debug_decompose(int32_t n_pixels, int32_t n_refs, int32_t num_sms, int32_t* grid,
+                            int64_t* cta_begin /* num_sms+1 entries or NULL */, int32_t* max_segments);
+/* kernel launches issued by this handle since creation (for bench.py's gpu_launches) */
+int64_t vosprop_launch_count(const vosprop_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOS_PROP_H_ */

@@ -1,0 +1,395 @@
+// libvosprop: C ABI (include/vos_prop.h) over the kernels in kernels.cuh.
+// Host side only: engine state (ring buffer, TMA descriptors, scratch), argument checking,
+// launch plumbing.  No CPU fallback anywhere: without an sm_100 device vosprop_create() fails.
+#include "../../include/vos_prop.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "decompose.h"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define VOS_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(VOSPROP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace
+
+struct vosprop_engine {
+    vosprop_config cfg{};
+    int num_sms = 0;
+    int p_pad_cap = 0;      // ring rows per slot at capacity
+    // geometry of the current video
+    int H_d = 0, W_d = 0, H = 0, W = 0, d = 0, P = 0, p_pad = 0;
+    __nv_bfloat16* ring_hi = nullptr;
+    __nv_bfloat16* ring_lo = nullptr;
+    float* meta = nullptr;
+    float* partials = nullptr;
+    size_t partial_records = 0;
+    CUtensorMap tmap_hi{}, tmap_lo{};
+    EncodeTiledFn encode = nullptr;
+    std::vector<int> slot_frame;
+    std::vector<char> slot_labels;
+    int64_t launches = 0;
+    bool attrs_set = false;
+};
+
+namespace {
+
+int encode_maps(vosprop_engine* e) {
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(vosk::kK),
+                                static_cast<cuuint64_t>(e->cfg.ring_slots) * static_cast<cuuint64_t>(e->p_pad)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(vosk::kK) * 2};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(vosk::kKC), static_cast<cuuint32_t>(vosk::kTile)};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r1 = e->encode(&e->tmap_hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, e->ring_hi, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = e->encode(&e->tmap_lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, e->ring_lo, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS)
+        return fail(VOSPROP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
+    return VOSPROP_OK;
+}
+
+template <int D>
+int launch_affinity(vosprop_engine* e, const vosk::AffinityParams& prm, int grid, int kernel, cudaStream_t st) {
+    if (kernel == VOSPROP_KERNEL_TC) {
+        VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kSmemTc));
+        vosk::vos_affinity_tc<D><<<grid, vosk::kTcThreads, vosk::kSmemTc, st>>>(e->tmap_hi, e->tmap_lo, prm);
+    } else {
+        VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_simt<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kSmemSimt));
+        vosk::vos_affinity_simt<D><<<grid, vosk::kSimtThreads, vosk::kSmemSimt, st>>>(prm);
+    }
+    VOS_CUDA(cudaGetLastError());
+    return VOSPROP_OK;
+}
+
+int dispatch_affinity(vosprop_engine* e, const vosk::AffinityParams& prm, int grid, int kernel, cudaStream_t st) {
+    const int d = e->d;
+    if (d <= 2) return launch_affinity<2>(e, prm, grid, kernel, st);
+    if (d <= 3) return launch_affinity<3>(e, prm, grid, kernel, st);
+    if (d <= 4) return launch_affinity<4>(e, prm, grid, kernel, st);
+    if (d <= 6) return launch_affinity<6>(e, prm, grid, kernel, st);
+    if (d <= 8) return launch_affinity<8>(e, prm, grid, kernel, st);
+    if (d <= 11) return launch_affinity<11>(e, prm, grid, kernel, st);
+    return launch_affinity<14>(e, prm, grid, kernel, st);
+}
+
+int check_frame(const vosprop_engine* e, int frame_idx) {
+    if (!e) return fail(VOSPROP_ERR_INVALID, "null engine");
+    if (e->P == 0) return fail(VOSPROP_ERR_STATE, "vosprop_reset() has not been called");
+    if (frame_idx < 0) return fail(VOSPROP_ERR_INVALID, "negative frame index %d", frame_idx);
+    return VOSPROP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* vosprop_last_error(void) { return g_err; }
+int vosprop_abi_version(void) { return VOSPROP_ABI_VERSION; }
+
+int vosprop_create(const vosprop_config* cfg, vosprop_engine** out) {
+    if (!cfg || !out) return fail(VOSPROP_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->max_pixels <= 0 || cfg->ring_slots < 2 || cfg->max_fullres_pixels < 0)
+        return fail(VOSPROP_ERR_INVALID, "bad config: max_pixels=%d ring_slots=%d", cfg->max_pixels, cfg->ring_slots);
+    int n_dev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n_dev);
+    if (ce != cudaSuccess || n_dev == 0)
+        return fail(VOSPROP_ERR_UNSUPPORTED, "no CUDA device (%s); libvosprop has no CPU fallback",
+                    ce == cudaSuccess ? "count = 0" : cudaGetErrorString(ce));
+    if (cfg->device < 0 || cfg->device >= n_dev) return fail(VOSPROP_ERR_INVALID, "device %d out of range", cfg->device);
+    cudaDeviceProp prop;
+    VOS_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(VOSPROP_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device,
+                    prop.major, prop.minor);
+    VOS_CUDA(cudaSetDevice(cfg->device));
+    vosprop_engine* e = new (std::nothrow) vosprop_engine();
+    if (!e) return fail(VOSPROP_ERR_INVALID, "out of host memory");
+    e->cfg = *cfg;
+    e->num_sms = prop.multiProcessorCount;
+    e->p_pad_cap = (cfg->max_pixels + vosk::kTile - 1) / vosk::kTile * vosk::kTile;
+    e->slot_frame.assign(cfg->ring_slots, -1);
+    e->slot_labels.assign(cfg->ring_slots, 0);
+
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    ce = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (ce != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+        delete e;
+        return fail(VOSPROP_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    }
+    e->encode = reinterpret_cast<EncodeTiledFn>(fn);
+
+    const size_t rows = static_cast<size_t>(cfg->ring_slots) * e->p_pad_cap;
+    const int tiles_cap = e->p_pad_cap / vosk::kTile;
+    e->partial_records = static_cast<size_t>(e->num_sms) * ((tiles_cap + e->num_sms - 1) / e->num_sms + 2) * 2;
+    cudaError_t a1 = cudaMalloc(&e->ring_hi, rows * vosk::kK * 2);
+    cudaError_t a2 = cudaMalloc(&e->ring_lo, rows * vosk::kK * 2);
+    cudaError_t a3 = cudaMalloc(&e->meta, rows * vosk::kMetaFloats * 4);
+    cudaError_t a4 = cudaMalloc(&e->partials, e->partial_records * vosk::kPartFloats * 4);
+    if (a1 != cudaSuccess || a2 != cudaSuccess || a3 != cudaSuccess || a4 != cudaSuccess) {
+        vosprop_destroy(e);
+        return fail(VOSPROP_ERR_CUDA, "cudaMalloc of the reference-memory ring failed (%zu rows)", rows);
+    }
+    // pad rows are read by TMA (and masked in the epilogue); keep them finite
+    cudaMemset(e->ring_hi, 0, rows * vosk::kK * 2);
+    cudaMemset(e->ring_lo, 0, rows * vosk::kK * 2);
+    cudaMemset(e->meta, 0, rows * vosk::kMetaFloats * 4);
+    ce = cudaDeviceSynchronize();
+    if (ce != cudaSuccess) {
+        vosprop_destroy(e);
+        return fail(VOSPROP_ERR_CUDA, "ring initialisation failed: %s", cudaGetErrorString(ce));
+    }
+    *out = e;
+    return VOSPROP_OK;
+}
+
+void vosprop_destroy(vosprop_engine* e) {
+    if (!e) return;
+    cudaFree(e->ring_hi);
+    cudaFree(e->ring_lo);
+    cudaFree(e->meta);
+    cudaFree(e->partials);
+    delete e;
+}
+
+int vosprop_reset(vosprop_engine* e, int32_t H_d, int32_t W_d, int32_t H, int32_t W, int32_t d, void* stream) {
+    if (!e) return fail(VOSPROP_ERR_INVALID, "null engine");
+    if (H_d <= 0 || W_d <= 0 || H <= 0 || W <= 0) return fail(VOSPROP_ERR_INVALID, "bad geometry %dx%d / %dx%d", H_d, W_d, H, W);
+    if (d < 1 || d > VOSPROP_MAX_CLASSES) return fail(VOSPROP_ERR_UNSUPPORTED, "d=%d classes; supported 1..%d", d, VOSPROP_MAX_CLASSES);
+    const int64_t P = static_cast<int64_t>(H_d) * W_d;
+    if (P > e->cfg.max_pixels) return fail(VOSPROP_ERR_UNSUPPORTED, "%lld pixels > engine capacity %d", (long long)P, e->cfg.max_pixels);
+    if (W_d > 4096) return fail(VOSPROP_ERR_UNSUPPORTED, "W_d=%d too wide", W_d);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    e->H_d = H_d; e->W_d = W_d; e->H = H; e->W = W; e->d = d;
+    e->P = static_cast<int>(P);
+    e->p_pad = (e->P + vosk::kTile - 1) / vosk::kTile * vosk::kTile;
+    int rc = encode_maps(e);
+    if (rc) return rc;
+    std::fill(e->slot_frame.begin(), e->slot_frame.end(), -1);
+    std::fill(e->slot_labels.begin(), e->slot_labels.end(), 0);
+    const size_t n = static_cast<size_t>(e->cfg.ring_slots) * e->p_pad;
+    vosk::vos_init_meta<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(e->meta, e->cfg.ring_slots, e->p_pad, e->P, W_d);
+    VOS_CUDA(cudaGetLastError());
+    e->launches++;
+    return VOSPROP_OK;
+}
+
+int vosprop_append_features(vosprop_engine* e, int32_t frame_idx, const void* features, int32_t dtype,
+                            int32_t layout, void* stream) {
+    int rc = check_frame(e, frame_idx);
+    if (rc) return rc;
+    if (!features) return fail(VOSPROP_ERR_INVALID, "null features");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int slot = frame_idx % e->cfg.ring_slots;
+    const size_t row0 = static_cast<size_t>(slot) * e->p_pad;
+    const int P = e->P;
+    if (layout == VOSPROP_NCHW) {
+        const unsigned grid = (P + 31) / 32;
+        if (dtype == VOSPROP_F32) vosk::vos_append_nchw<float><<<grid, 256, 0, st>>>(static_cast<const float*>(features), e->ring_hi, e->ring_lo, P, row0);
+        else if (dtype == VOSPROP_F16) vosk::vos_append_nchw<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(features), e->ring_hi, e->ring_lo, P, row0);
+        else if (dtype == VOSPROP_BF16) vosk::vos_append_nchw<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(features), e->ring_hi, e->ring_lo, P, row0);
+        else return fail(VOSPROP_ERR_INVALID, "unknown dtype %d", dtype);
+    } else if (layout == VOSPROP_NHWC) {
+        const unsigned grid = static_cast<unsigned>((static_cast<size_t>(P) * (vosk::kK / 2) + 255) / 256);
+        if (dtype == VOSPROP_F32) vosk::vos_append_nhwc<float><<<grid, 256, 0, st>>>(static_cast<const float*>(features), e->ring_hi, e->ring_lo, P, row0);
+        else if (dtype == VOSPROP_F16) vosk::vos_append_nhwc<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(features), e->ring_hi, e->ring_lo, P, row0);
+        else if (dtype == VOSPROP_BF16) vosk::vos_append_nhwc<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(features), e->ring_hi, e->ring_lo, P, row0);
+        else return fail(VOSPROP_ERR_INVALID, "unknown dtype %d", dtype);
+    } else {
+        return fail(VOSPROP_ERR_INVALID, "unknown layout %d", layout);
+    }
+    VOS_CUDA(cudaGetLastError());
+    e->slot_frame[slot] = frame_idx;
+    e->slot_labels[slot] = 0;
+    e->launches++;
+    return VOSPROP_OK;
+}
+
+static int labels_target(vosprop_engine* e, int frame_idx, float** meta_slot) {
+    int rc = check_frame(e, frame_idx);
+    if (rc) return rc;
+    const int slot = frame_idx % e->cfg.ring_slots;
+    if (e->slot_frame[slot] != frame_idx)
+        return fail(VOSPROP_ERR_STATE, "frame %d is not in the ring (slot %d holds %d): append its features first", frame_idx, slot, e->slot_frame[slot]);
+    *meta_slot = e->meta + static_cast<size_t>(slot) * e->p_pad * vosk::kMetaFloats;
+    e->slot_labels[slot] = 1;
+    return VOSPROP_OK;
+}
+
+int vosprop_set_labels_index(vosprop_engine* e, int32_t frame_idx, const uint8_t* class_idx, void* stream) {
+    float* ms = nullptr;
+    int rc = labels_target(e, frame_idx, &ms);
+    if (rc) return rc;
+    if (!class_idx) return fail(VOSPROP_ERR_INVALID, "null class_idx");
+    vosk::vos_set_labels_index<<<(e->P + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(ms, class_idx, e->P);
+    VOS_CUDA(cudaGetLastError());
+    e->launches++;
+    return VOSPROP_OK;
+}
+
+int vosprop_set_labels_dense(vosprop_engine* e, int32_t frame_idx, const float* labels, void* stream) {
+    float* ms = nullptr;
+    int rc = labels_target(e, frame_idx, &ms);
+    if (rc) return rc;
+    if (!labels) return fail(VOSPROP_ERR_INVALID, "null labels");
+    vosk::vos_set_labels_dense<<<(e->P + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(ms, labels, e->P, e->d);
+    VOS_CUDA(cudaGetLastError());
+    e->launches++;
+    return VOSPROP_OK;
+}
+
+int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
+    if (!s) return fail(VOSPROP_ERR_INVALID, "null step");
+    int rc = check_frame(e, s->frame_idx);
+    if (rc) return rc;
+    if (s->n_refs < 1 || s->n_refs > VOSPROP_MAX_REFS) return fail(VOSPROP_ERR_INVALID, "n_refs=%d outside 1..%d", s->n_refs, VOSPROP_MAX_REFS);
+    if (!(s->temperature >= 0.f) || !std::isfinite(s->temperature))
+        return fail(VOSPROP_ERR_UNSUPPORTED, "temperature %g: only finite temperature >= 0 is supported", (double)s->temperature);
+    if (s->topk != 0) return fail(VOSPROP_ERR_UNSUPPORTED, "top-k mode is not built yet (topk=%d)", s->topk);
+    if (s->kernel != VOSPROP_KERNEL_TC && s->kernel != VOSPROP_KERNEL_SIMT) return fail(VOSPROP_ERR_INVALID, "unknown kernel %d", s->kernel);
+    if (s->out_mask_fullres && static_cast<int64_t>(e->H) * e->W > e->cfg.max_fullres_pixels && e->cfg.max_fullres_pixels > 0)
+        return fail(VOSPROP_ERR_UNSUPPORTED, "full-resolution frame larger than configured");
+    const int S = e->cfg.ring_slots;
+    const int q_slot = s->frame_idx % S;
+    if (e->slot_frame[q_slot] != s->frame_idx)
+        return fail(VOSPROP_ERR_STATE, "target frame %d is not in the ring: append its features first", s->frame_idx);
+
+    vosk::AffinityParams ap{};
+    ap.n_pixels = e->P; ap.p_pad = e->p_pad; ap.w_lowres = e->W_d; ap.n_refs = s->n_refs; ap.q_slot = q_slot;
+    ap.num_sms = e->num_sms;
+    for (int r = 0; r < s->n_refs; ++r) {
+        const int f = s->ref_frames[r];
+        if (f < 0) return fail(VOSPROP_ERR_INVALID, "negative reference frame %d", f);
+        const int slot = f % S;
+        if (e->slot_frame[slot] != f || !e->slot_labels[slot])
+            return fail(VOSPROP_ERR_STATE, "reference frame %d is not in the ring (slot %d holds frame %d, labels=%d); ring_slots=%d too small or labels never set",
+                        f, slot, e->slot_frame[slot], (int)e->slot_labels[slot], S);
+        if (slot == q_slot && s->write_labels)
+            return fail(VOSPROP_ERR_STATE, "reference frame %d aliases the target's ring slot", f);
+        ap.ref_slot[r] = slot;
+        const float sg = s->ref_sigma[r];
+        ap.ref_coef[r] = sg > 0.f ? static_cast<float>(1.4426950408889634 / (static_cast<double>(sg) * sg)) : 0.f;
+    }
+    ap.scale2 = static_cast<float>(static_cast<double>(s->temperature) * 1.4426950408889634);
+    ap.meta = e->meta; ap.partials = e->partials; ap.ring_hi = e->ring_hi; ap.ring_lo = e->ring_lo;
+    const vosd::Decomp dec = vosd::make_decomp(e->P, s->n_refs, e->num_sms);
+    if (static_cast<size_t>(dec.grid) * dec.max_segs * 2 > e->partial_records)
+        return fail(VOSPROP_ERR_UNSUPPORTED, "partial buffer too small (grid %d x segs %d)", dec.grid, dec.max_segs);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = dispatch_affinity(e, ap, dec.grid, s->kernel, st);
+    if (rc) return rc;
+
+    vosk::MergeParams mp{};
+    mp.n_pixels = e->P; mp.p_pad = e->p_pad; mp.w_lowres = e->W_d; mp.h_lowres = e->H_d; mp.n_refs = s->n_refs;
+    mp.num_sms = e->num_sms; mp.d = e->d; mp.H = e->H; mp.W = e->W; mp.q_slot = q_slot;
+    mp.write_labels = s->write_labels; mp.probability = s->probability_propagation;
+    mp.partials = e->partials; mp.meta = e->meta;
+    mp.out_prediction = s->out_prediction; mp.out_mask_lowres = s->out_mask_lowres; mp.out_mask_fullres = s->out_mask_fullres;
+    vosk::vos_merge_writeback<<<e->H_d, 128, e->W_d, st>>>(mp);
+    VOS_CUDA(cudaGetLastError());
+    if (s->write_labels) e->slot_labels[q_slot] = 1;
+    e->launches += 2;
+    return VOSPROP_OK;
+}
+
+int vosprop_sample_frames(int32_t frame_idx, int32_t take_range, int32_t num_refs, int32_t* out_idx) {
+    // src/model/predict.py:74-89
+    if (!out_idx) return fail(VOSPROP_ERR_INVALID, "null out_idx");
+    if (frame_idx < 0) return fail(VOSPROP_ERR_INVALID, "negative frame index");
+    if (frame_idx <= num_refs) {
+        if (frame_idx > VOSPROP_MAX_REFS) return fail(VOSPROP_ERR_UNSUPPORTED, "more than %d references", VOSPROP_MAX_REFS);
+        for (int i = 0; i < frame_idx; ++i) out_idx[i] = i;
+        return frame_idx;
+    }
+    const int dense_num = 4 - 1;  // Config.CONTINUOUS_FRAME - 1
+    const int sparse_num = num_refs - dense_num;
+    if (sparse_num < 0) return fail(VOSPROP_ERR_INVALID, "num_refs=%d < 3 with frame_idx=%d: the reference raises ValueError here (np.linspace with a negative count)", num_refs, frame_idx);
+    if (num_refs > VOSPROP_MAX_REFS) return fail(VOSPROP_ERR_UNSUPPORTED, "more than %d references", VOSPROP_MAX_REFS);
+    const int ref_end = frame_idx - dense_num - 1;
+    const int ref_start = ref_end - take_range > 0 ? ref_end - take_range : 0;
+    // numpy.linspace(ref_start, ref_end, sparse_num) in float64, then astype(int) (truncation)
+    const double start = ref_start, stop = ref_end, delta = stop - start;
+    const int div = sparse_num - 1;
+    int n = 0;
+    for (int i = 0; i < sparse_num; ++i) {
+        volatile double y;  // volatile: keep the separately rounded multiply and add of numpy (no FMA contraction)
+        if (div > 0) {
+            const double step = delta / div;
+            if (step == 0.0) { y = static_cast<double>(i) / div; y = y * delta; }
+            else y = static_cast<double>(i) * step;
+        } else {
+            y = static_cast<double>(i) * delta;
+        }
+        y = y + start;
+        if (sparse_num > 1 && i == sparse_num - 1) y = stop;
+        out_idx[n++] = static_cast<int32_t>(y);
+    }
+    for (int j = 0; j < dense_num; ++j) out_idx[n++] = frame_idx - dense_num + j;
+    return n;
+}
+
+int vosprop_plan_step(int32_t frame_idx, int32_t take_range, int32_t num_refs, float sigma_dense, float sigma_sparse,
+                      int32_t probability_propagation, vosprop_step* step) {
+    if (!step) return fail(VOSPROP_ERR_INVALID, "null step");
+    const int n = vosprop_sample_frames(frame_idx, take_range, num_refs, step->ref_frames);
+    if (n < 0) return n;
+    step->frame_idx = frame_idx;
+    step->n_refs = n;
+    // src/model/predict.py:59-66: frame_idx > 15 -> refs[:-4] sparse sigma, refs[-4:] dense sigma; else all dense
+    for (int r = 0; r < n; ++r) {
+        float sg = sigma_dense;
+        if (frame_idx > 15 && r < n - 4) sg = sigma_sparse;
+        step->ref_sigma[r] = probability_propagation ? 0.f : sg;
+    }
+    step->probability_propagation = probability_propagation;
+    return VOSPROP_OK;
+}
+
+int vosprop_ring_slots(const vosprop_engine* e) { return e ? e->cfg.ring_slots : VOSPROP_ERR_INVALID; }
+int vosprop_num_sms(const vosprop_engine* e) { return e ? e->num_sms : VOSPROP_ERR_INVALID; }
+int64_t vosprop_launch_count(const vosprop_engine* e) { return e ? e->launches : -1; }
+
+int vosprop_debug_decompose(int32_t n_pixels, int32_t n_refs, int32_t num_sms, int32_t* grid, int64_t* cta_begin,
+                            int32_t* max_segments) {
+    if (n_pixels <= 0 || n_refs <= 0 || num_sms <= 0) return fail(VOSPROP_ERR_INVALID, "bad decomposition query");
+    const vosd::Decomp d = vosd::make_decomp(n_pixels, n_refs, num_sms);
+    if (grid) *grid = d.grid;
+    if (max_segments) *max_segments = d.max_segs;
+    if (cta_begin)
+        for (int c = 0; c <= d.grid; ++c) cta_begin[c] = vosd::cta_begin(d, c);
+    return VOSPROP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,173 @@
+"""PropagationEngine: torch-facing wrapper of one libvosprop handle.
+
+PyTorch is used for device memory and streams only; all arithmetic of the propagation path runs
+in the CUDA kernels of libvosprop.so (csrc/).  One engine per video sequence in flight.  Every
+method is stream-ordered on torch's current stream and never synchronises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import _capi as capi
+
+CONTINUOUS_FRAME = 4          # src/config.py:13
+DEFAULT_RING_SLOTS = 48       # >= frame_range(40) + CONTINUOUS_FRAME + 1, SURVEY.md P5
+
+_DTYPES = {torch.float32: capi.F32, torch.float16: capi.F16, torch.bfloat16: capi.BF16}
+
+
+def sample_frames(frame_idx: int, take_range: int, num_refs: int) -> List[int]:
+    """src/model/predict.py:74-89, computed by the C library (host arithmetic, no GPU needed).
+    Raises ValueError where the reference's np.linspace does (num_refs < 3 and frame_idx > num_refs)."""
+    buf = (C.c_int32 * capi.MAX_REFS)()
+    n = capi.lib().vosprop_sample_frames(frame_idx, take_range, num_refs, buf)
+    if n == capi.ERR_INVALID:
+        raise ValueError(capi.lib().vosprop_last_error().decode())
+    capi.check(n)
+    return list(buf[:n])
+
+
+def plan_refs(frame_idx: int, take_range: int, num_refs: int, sigma_dense: float, sigma_sparse: float,
+              probability_propagation: bool):
+    """(ref_frames, ref_sigmas) for one step: sample_frames + the sigma rule of predict.py:59-66."""
+    st = capi.Step()
+    rc = capi.lib().vosprop_plan_step(frame_idx, take_range, num_refs, sigma_dense, sigma_sparse,
+                                      int(probability_propagation), C.byref(st))
+    if rc == capi.ERR_INVALID:
+        raise ValueError(capi.lib().vosprop_last_error().decode())
+    capi.check(rc)
+    return list(st.ref_frames[:st.n_refs]), list(st.ref_sigma[:st.n_refs])
+
+
+def required_ring_slots(frame_range: int, ref_num: int) -> int:
+    """Slots needed so that every frame sample_frames can pick is still resident, plus the target."""
+    return max(frame_range + CONTINUOUS_FRAME, ref_num) + 1
+
+
+class PropagationEngine:
+    def __init__(self, max_pixels: int, ring_slots: int = DEFAULT_RING_SLOTS, max_fullres_pixels: int = 0,
+                 device: Optional[torch.device] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('PropagationEngine needs a CUDA device (sm_100a); there is no CPU fallback')
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self._lib = capi.lib()
+        self._h = C.c_void_p()
+        cfg = capi.Config(self.device.index or 0, int(max_pixels), int(ring_slots), int(max_fullres_pixels))
+        with torch.cuda.device(self.device):
+            capi.check(self._lib.vosprop_create(C.byref(cfg), C.byref(self._h)))
+        self.ring_slots = ring_slots
+        self.max_pixels = max_pixels
+        self.geom = None
+
+    def close(self):
+        if getattr(self, '_h', None) and self._h.value:
+            self._lib.vosprop_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self) -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def num_sms(self) -> int:
+        return self._lib.vosprop_num_sms(self._h)
+
+    @property
+    def launch_count(self) -> int:
+        return self._lib.vosprop_launch_count(self._h)
+
+    # ------------------------------------------------------------------ per-video state
+    def reset(self, H_d: int, W_d: int, H: int, W: int, d: int):
+        capi.check(self._lib.vosprop_reset(self._h, H_d, W_d, H, W, d, self._stream()))
+        self.geom = (H_d, W_d, H, W, d)
+
+    def append(self, frame_idx: int, features: torch.Tensor):
+        """features: (K,H_d,W_d) or (1,K,H_d,W_d), fp32/fp16/bf16, standard or channels_last."""
+        if features.dim() == 4:
+            if features.shape[0] != 1:
+                raise ValueError('append() takes one frame')
+            features = features[0]
+        H_d, W_d = self.geom[0], self.geom[1]
+        if tuple(features.shape) != (capi.FEAT_DIM, H_d, W_d):
+            raise ValueError(f'expected ({capi.FEAT_DIM},{H_d},{W_d}) features, got {tuple(features.shape)}')
+        if features.dtype not in _DTYPES or not features.is_cuda:
+            raise TypeError(f'features must be a CUDA fp32/fp16/bf16 tensor, got {features.dtype} on {features.device}')
+        if features.is_contiguous():
+            layout = capi.NCHW
+        elif features.permute(1, 2, 0).is_contiguous():
+            layout = capi.NHWC
+        else:
+            features, layout = features.contiguous(), capi.NCHW
+        capi.check(self._lib.vosprop_append_features(self._h, frame_idx, C.c_void_p(features.data_ptr()),
+                                                     _DTYPES[features.dtype], layout, self._stream()))
+        features.record_stream(torch.cuda.current_stream(self.device))
+
+    def set_labels_index(self, frame_idx: int, class_idx: torch.Tensor):
+        P = self.geom[0] * self.geom[1]
+        class_idx = class_idx.reshape(-1).to(device=self.device, dtype=torch.uint8).contiguous()
+        if class_idx.numel() != P:
+            raise ValueError(f'expected {P} labels, got {class_idx.numel()}')
+        capi.check(self._lib.vosprop_set_labels_index(self._h, frame_idx, C.c_void_p(class_idx.data_ptr()), self._stream()))
+        class_idx.record_stream(torch.cuda.current_stream(self.device))
+
+    def set_labels_dense(self, frame_idx: int, labels: torch.Tensor):
+        P, d = self.geom[0] * self.geom[1], self.geom[4]
+        labels = labels.reshape(labels.shape[0], -1).to(device=self.device, dtype=torch.float32).contiguous()
+        if tuple(labels.shape) != (d, P):
+            raise ValueError(f'expected ({d},{P}) labels, got {tuple(labels.shape)}')
+        capi.check(self._lib.vosprop_set_labels_dense(self._h, frame_idx, C.c_void_p(labels.data_ptr()), self._stream()))
+        labels.record_stream(torch.cuda.current_stream(self.device))
+
+    # ------------------------------------------------------------------ the hot path
+    def propagate(self, frame_idx: int, ref_frames: Sequence[int], ref_sigmas: Sequence[float],
+                  temperature: float = 1.0, probability_propagation: bool = False, write_labels: bool = True,
+                  kernel: int = capi.KERNEL_TC, want_prediction: bool = True, want_lowres: bool = True,
+                  want_fullres: bool = True, out_fullres: Optional[torch.Tensor] = None,
+                  out_prediction: Optional[torch.Tensor] = None, topk: int = 0) -> Dict[str, torch.Tensor]:
+        H_d, W_d, H, W, d = self.geom
+        P = H_d * W_d
+        st = capi.Step()
+        st.frame_idx = frame_idx
+        st.n_refs = len(ref_frames)
+        if len(ref_frames) > capi.MAX_REFS or len(ref_frames) != len(ref_sigmas):
+            raise ValueError('bad reference list')
+        for i, (f, s) in enumerate(zip(ref_frames, ref_sigmas)):
+            st.ref_frames[i] = int(f)
+            st.ref_sigma[i] = float(s) if s is not None else 0.0
+        st.temperature = float(temperature)
+        st.probability_propagation = int(probability_propagation)
+        st.write_labels = int(write_labels)
+        st.topk = int(topk)
+        st.kernel = int(kernel)
+        out: Dict[str, torch.Tensor] = {}
+        if want_prediction or out_prediction is not None:
+            pred = out_prediction if out_prediction is not None else torch.empty((d, P), dtype=torch.float32, device=self.device)
+            assert pred.is_contiguous() and pred.dtype == torch.float32 and pred.numel() == d * P
+            st.out_prediction = pred.data_ptr()
+            out['prediction'] = pred
+        if want_lowres:
+            low = torch.empty((P,), dtype=torch.uint8, device=self.device)
+            st.out_mask_lowres = low.data_ptr()
+            out['mask_lowres'] = low
+        if want_fullres or out_fullres is not None:
+            full = out_fullres if out_fullres is not None else torch.empty((H, W), dtype=torch.uint8, device=self.device)
+            assert full.is_contiguous() and full.dtype == torch.uint8 and full.numel() == H * W
+            st.out_mask_fullres = full.data_ptr()
+            out['mask'] = full
+        capi.check(self._lib.vosprop_propagate(self._h, C.byref(st), self._stream()))
+        return out
+
+    def step(self, frame_idx: int, frame_range: int, ref_num: int, sigma_1: float, sigma_2: float,
+             temperature: float, probability_propagation: bool, **kw) -> Dict[str, torch.Tensor]:
+        """One call of the reference's predict() + write-back for target `frame_idx`."""
+        refs, sig = plan_refs(frame_idx, frame_range, ref_num, sigma_1, sigma_2, probability_propagation)
+        return self.propagate(frame_idx, refs, sig, temperature, probability_propagation, **kw)
