@@ -118,6 +118,15 @@ int vosprop_debug_decompose(int32_t n_pixels, int32_t n_refs, int32_t num_sms, i
 /* kernel launches issued by this handle since creation (for bench.py's gpu_launches) */
 int64_t vosprop_launch_count(const vosprop_engine* e);
 
+/* Per-kernel device timing for bench.py's roofline: when enabled, every append / affinity / merge
+ * launch is bracketed by CUDA events recorded on the launching stream (capacity = launches kept).
+ * vosprop_timing_read() synchronises on the recorded events, returns the summed milliseconds and
+ * launch counts per kernel class since the last read, and clears the log.
+ * totals_ms[3] / counts[3] are indexed by enum vosprop_timed_kernel. */
+enum vosprop_timed_kernel { VOSPROP_T_APPEND = 0, VOSPROP_T_AFFINITY = 1, VOSPROP_T_MERGE = 2 };
+int vosprop_timing_enable(vosprop_engine* e, int32_t capacity);
+int vosprop_timing_read(vosprop_engine* e, double* totals_ms, int64_t* counts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@ sys.path.insert(0, str(REPO))
 
 from oracle import propagation_oracle as O  # noqa: E402
 from oracle import reference_harness as RH  # noqa: E402
+from oracle.fixtures import seeded_state_dict  # noqa: E402
 
 OUT = REPO / 'tests' / 'golden'
 
@@ -49,27 +50,6 @@ GEN_KEYS = ('T', 'H', 'W', 'n_objects', 'seed', 'feat_scale')
 
 def checksum(t: torch.Tensor) -> str:
     return hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest()
-
-
-def seeded_state_dict(template: dict) -> dict:
-    """Deterministic weights keyed by parameter name (so any module with the same keys/shapes
-    gets the same values regardless of construction order)."""
-    out = {}
-    for k in sorted(template):
-        v = template[k]
-        g = torch.Generator().manual_seed(int(hashlib.sha256(k.encode()).hexdigest()[:8], 16))
-        if k.endswith('num_batches_tracked'):
-            out[k] = torch.zeros_like(v)
-        elif k.endswith('running_var'):
-            out[k] = torch.rand(v.shape, generator=g) + 0.5
-        elif k.endswith('running_mean') or k.endswith('bias'):
-            out[k] = torch.randn(v.shape, generator=g) * 0.1
-        elif v.dim() == 1:
-            out[k] = torch.rand(v.shape, generator=g) * 0.5 + 0.75
-        else:
-            fan_in = v[0].numel()
-            out[k] = torch.randn(v.shape, generator=g) * (1.0 / fan_in) ** 0.5
-    return out
 
 
 def main():

@@ -144,13 +144,16 @@ def predict(ref: torch.Tensor, target: torch.Tensor, ref_label: torch.Tensor,
             sigma_dense: Optional[float], sigma_sparse: Optional[float], frame_idx: int,
             take_range: int, ref_num: int, temperature: float,
             probability_propagation: bool, chunk: Optional[int] = None,
-            topk: Optional[int] = None, return_topk_idx: bool = False):
+            topk: Optional[int] = None, return_topk_idx: bool = False,
+            weights: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
     """Label propagation for one target frame.
 
     ref (T,K,H,W) fp32, target (K,H,W), ref_label (d,T,P) -> prediction (d,P) fp32.
     Follows src/model/predict.py:40-70 line by line; the (P,P) priors are rebuilt per column
     chunk from (sigma, H, W) instead of being passed in.
 
+    ``weights``: optional precomputed (weight_dense, weight_sparse) (P,P) matrices, as the
+    reference passes them (built once per video by prepare_first_frame, predict.py:117-118).
     ``chunk``: process target pixels in column blocks of this size (softmax over dim 0 is
     per-column, so chunking is exact up to GEMM blocking).
     ``topk``: EXTENSION (not in the reference): the softmax of predict.py:55 is
@@ -187,9 +190,9 @@ def predict(ref: torch.Tensor, target: torch.Tensor, ref_label: torch.Tensor,
                 topk_idx[cs] = torch.sort(S, dim=0, descending=True, stable=True).indices[:topk].t()
         if use_prior:                                                    # :59-66
             S = S.view(R, P, -1)
-            w_dense = spatial_weight((H, W), sigma_dense, cs)
+            w_dense = weights[0][:, cs] if weights else spatial_weight((H, W), sigma_dense, cs)
             if frame_idx > DENSE_SWITCH_FRAME:
-                w_sparse = spatial_weight((H, W), sigma_sparse, cs)
+                w_sparse = weights[1][:, cs] if weights else spatial_weight((H, W), sigma_sparse, cs)
                 S[:-CONTINUOUS_FRAME] *= w_sparse
                 S[-CONTINUOUS_FRAME:] *= w_dense
             else:

@@ -57,8 +57,28 @@ struct vosprop_engine {
     std::vector<int> slot_frame;
     std::vector<char> slot_labels;
     int64_t launches = 0;
-    bool attrs_set = false;
+    // optional per-kernel timing (bench.py roofline)
+    std::vector<cudaEvent_t> ev;      // 2 events per timed launch
+    std::vector<int> ev_kind;
+    size_t ev_used = 0;
+    bool timing = false;
 };
+
+namespace {
+struct TimedLaunch {   // RAII: records an event pair around one kernel launch when timing is on
+    vosprop_engine* e; cudaStream_t st; bool on;
+    TimedLaunch(vosprop_engine* e_, int kind, cudaStream_t st_) : e(e_), st(st_), on(false) {
+        if (e->timing && e->ev_used + 2 <= e->ev.size()) {
+            on = true;
+            e->ev_kind[e->ev_used / 2] = kind;
+            cudaEventRecord(e->ev[e->ev_used], st);
+        }
+    }
+    ~TimedLaunch() {
+        if (on) { cudaEventRecord(e->ev[e->ev_used + 1], st); e->ev_used += 2; }
+    }
+};
+}  // namespace
 
 namespace {
 
@@ -181,6 +201,7 @@ void vosprop_destroy(vosprop_engine* e) {
     cudaFree(e->ring_lo);
     cudaFree(e->meta);
     cudaFree(e->partials);
+    for (cudaEvent_t ev : e->ev) cudaEventDestroy(ev);
     delete e;
 }
 
@@ -215,6 +236,7 @@ int vosprop_append_features(vosprop_engine* e, int32_t frame_idx, const void* fe
     const int slot = frame_idx % e->cfg.ring_slots;
     const size_t row0 = static_cast<size_t>(slot) * e->p_pad;
     const int P = e->P;
+    TimedLaunch timed(e, VOSPROP_T_APPEND, st);
     if (layout == VOSPROP_NCHW) {
         const unsigned grid = (P + 31) / 32;
         if (dtype == VOSPROP_F32) vosk::vos_append_nchw<float><<<grid, 256, 0, st>>>(static_cast<const float*>(features), e->ring_hi, e->ring_lo, P, row0);
@@ -308,7 +330,10 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     if (static_cast<size_t>(dec.grid) * dec.max_segs * 2 > e->partial_records)
         return fail(VOSPROP_ERR_UNSUPPORTED, "partial buffer too small (grid %d x segs %d)", dec.grid, dec.max_segs);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    rc = dispatch_affinity(e, ap, dec.grid, s->kernel, st);
+    {
+        TimedLaunch timed(e, VOSPROP_T_AFFINITY, st);
+        rc = dispatch_affinity(e, ap, dec.grid, s->kernel, st);
+    }
     if (rc) return rc;
 
     vosk::MergeParams mp{};
@@ -317,7 +342,10 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     mp.write_labels = s->write_labels; mp.probability = s->probability_propagation;
     mp.partials = e->partials; mp.meta = e->meta;
     mp.out_prediction = s->out_prediction; mp.out_mask_lowres = s->out_mask_lowres; mp.out_mask_fullres = s->out_mask_fullres;
-    vosk::vos_merge_writeback<<<e->H_d, 128, e->W_d, st>>>(mp);
+    {
+        TimedLaunch timed(e, VOSPROP_T_MERGE, st);
+        vosk::vos_merge_writeback<<<e->H_d, 128, e->W_d, st>>>(mp);
+    }
     VOS_CUDA(cudaGetLastError());
     if (s->write_labels) e->slot_labels[q_slot] = 1;
     e->launches += 2;
@@ -380,6 +408,34 @@ int vosprop_plan_step(int32_t frame_idx, int32_t take_range, int32_t num_refs, f
 int vosprop_ring_slots(const vosprop_engine* e) { return e ? e->cfg.ring_slots : VOSPROP_ERR_INVALID; }
 int vosprop_num_sms(const vosprop_engine* e) { return e ? e->num_sms : VOSPROP_ERR_INVALID; }
 int64_t vosprop_launch_count(const vosprop_engine* e) { return e ? e->launches : -1; }
+
+int vosprop_timing_enable(vosprop_engine* e, int32_t capacity) {
+    if (!e || capacity < 0) return fail(VOSPROP_ERR_INVALID, "bad timing request");
+    while (e->ev.size() < static_cast<size_t>(capacity) * 2) {
+        cudaEvent_t ev;
+        VOS_CUDA(cudaEventCreate(&ev));
+        e->ev.push_back(ev);
+    }
+    e->ev_kind.resize(e->ev.size() / 2);
+    e->ev_used = 0;
+    e->timing = capacity > 0;
+    return VOSPROP_OK;
+}
+
+int vosprop_timing_read(vosprop_engine* e, double* totals_ms, int64_t* counts) {
+    if (!e || !totals_ms || !counts) return fail(VOSPROP_ERR_INVALID, "null argument");
+    for (int k = 0; k < 3; ++k) { totals_ms[k] = 0.0; counts[k] = 0; }
+    for (size_t i = 0; i + 1 < e->ev_used; i += 2) {
+        VOS_CUDA(cudaEventSynchronize(e->ev[i + 1]));
+        float ms = 0.f;
+        VOS_CUDA(cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]));
+        const int k = e->ev_kind[i / 2];
+        totals_ms[k] += ms;
+        counts[k] += 1;
+    }
+    e->ev_used = 0;
+    return VOSPROP_OK;
+}
 
 int vosprop_debug_decompose(int32_t n_pixels, int32_t n_refs, int32_t num_sms, int32_t* grid, int64_t* cta_begin,
                             int32_t* max_segments) {

@@ -1,0 +1,84 @@
+"""`inference` command: same click surface and `inference_command_impl` signature as the
+reference's src/inference.py:18-113."""
+from pathlib import Path
+
+import click
+import torch
+import torch.utils.data
+from loguru import logger
+
+from src.config import Config
+from src.model.vos_net import VOSNet
+from src.utils.datasets import InferenceDataset
+from src.utils.inference_utils import (inference_2_scale, inference_3_scale, inference_hor_flip,
+                                       inference_multimodel, inference_single, inference_ver_flip)
+from src.utils.utils import load_model
+
+
+@click.command(name='inference')
+@click.option('--ref_num', '-n', type=int, default=9, help='Number of reference frames for inference.')
+@click.option('--data', '-d', type=click.Path(file_okay=False, dir_okay=True), required=True,
+              help='Path to inference dataset folder.')
+@click.option('--resume', '-r', type=click.Path(file_okay=True, dir_okay=False), required=True,
+              help='Path to the trained checkpoint.')
+@click.option('--model', '-m', type=click.Choice(['resnet18', 'resnet50', 'resnet101', 'facebook']), default='resnet50',
+              help='Network architecture, resnet18, resnet50, resnet101 or facebook.')
+@click.option('--temperature', '-t', type=float, default=1.0, help='Temperature parameter.')
+@click.option('--frame_range', type=int, default=40, help='Range of frames for inference.')
+@click.option('--sigma_1', type=float, default=8.0, help='Smaller sigma in the motion model for dense spatial weight')
+@click.option('--sigma_2', type=float, default=21.0, help='Larger sigma in the motion model for dense spatial weight.')
+@click.option('--save', '-s', type=click.Path(file_okay=False, dir_okay=True), required=True,
+              help='Path to save predictions.')
+@click.option('--device', type=click.Choice(['cpu', 'cuda']), default='cuda', help='Device to run computing on.')
+@click.option('--inference-strategy',
+              type=click.Choice(['single', 'hor-flip', 'vert-flip', '2-scale', 'multimodel', 'hor-2-scale', '3-scale']),
+              default='single', help='Inference strategy.')
+@click.option('--additional-model', type=click.Path(file_okay=True, dir_okay=False), required=False,
+              help='Path to the additional checkpoint.')
+@click.option('--additional-model-type', type=click.STRING, required=False, default='resnet50',
+              help='Type of additional model type.')
+@click.option('--probability/--no-probability', default=False, required=False,
+              help='Should probability or labels be propagated.')
+@click.option('--scale', default=1.15, required=False, type=click.FLOAT, help='Scale for 2nd image in 2-scale strategy.')
+@click.option('--fusion', default='mean', type=click.Choice(['maximum', 'minimum', 'mean']),
+              help='Fusion operation for probability propagation.')
+def inference_command(ref_num, data, resume, model, temperature, frame_range, sigma_1, sigma_2, save, device,
+                      inference_strategy, additional_model, additional_model_type, probability, scale, fusion):
+    inference_command_impl(ref_num, data, resume, model, temperature, frame_range, sigma_1, sigma_2, save, device,
+                           inference_strategy, additional_model, additional_model_type, probability, scale, fusion)
+
+
+def _load_net(arch, checkpoint):
+    net = load_model(VOSNet(model=arch), checkpoint)
+    return net.to(Config.DEVICE).eval()
+
+
+def inference_command_impl(ref_num, data, resume, model, temperature, frame_range, sigma_1, sigma_2, save, device,
+                           inference_strategy, additional_resume, additional_model_type, probability_propagation,
+                           scale, reduction, disable=False):
+    if Config.DEVICE.type != device:
+        Config.DEVICE = torch.device(device)
+    model = _load_net(model, resume)
+    additional_model = _load_net(additional_model_type, additional_resume) if inference_strategy == 'multimodel' else None
+
+    dataset = InferenceDataset(str(Path(data) / 'JPEGImages/480p'), disable=disable,
+                               inference_strategy=inference_strategy, scale=scale)
+    loader = torch.utils.data.DataLoader(dataset, batch_size=1, shuffle=False, num_workers=1, pin_memory=True)
+    annotation_dir = Path(data) / 'Annotations/480p'
+    last_video = sorted(annotation_dir.glob('*'))[0].name
+    common = (loader, len(dataset), annotation_dir, last_video, save, sigma_1, sigma_2, frame_range, ref_num,
+              temperature, probability_propagation)
+    with torch.no_grad():
+        if inference_strategy == 'single':
+            inference_single(model, *common, disable)
+        elif inference_strategy == 'hor-flip':
+            inference_hor_flip(model, *common, reduction, disable)
+        elif inference_strategy == 'vert-flip':
+            inference_ver_flip(model, *common, reduction, disable)
+        elif inference_strategy in ('2-scale', 'hor-2-scale'):
+            inference_2_scale(model, *common, scale, reduction, inference_strategy == 'hor-2-scale', disable)
+        elif inference_strategy == 'multimodel':
+            inference_multimodel(model, additional_model, *common, reduction, disable)
+        elif inference_strategy == '3-scale':
+            inference_3_scale(model, *common, scale, disable)
+    logger.info('Inference done.')

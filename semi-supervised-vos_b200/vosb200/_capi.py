@@ -52,6 +52,8 @@ EXPORTS = {
     'vosprop_debug_decompose': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
                                            C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     'vosprop_launch_count': (C.c_int64, [C.c_void_p]),
+    'vosprop_timing_enable': (C.c_int, [C.c_void_p, C.c_int32]),
+    'vosprop_timing_read': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
 
 _lib = None

@@ -85,6 +85,16 @@ class PropagationEngine:
     def launch_count(self) -> int:
         return self._lib.vosprop_launch_count(self._h)
 
+    def enable_timing(self, capacity: int):
+        """Bracket every kernel launch with CUDA events (bench.py roofline); 0 disables."""
+        capi.check(self._lib.vosprop_timing_enable(self._h, int(capacity)))
+
+    def read_timing(self):
+        """{'append'|'affinity'|'merge': (total_ms, launches)} since the last read (synchronises)."""
+        tot, cnt = (C.c_double * 3)(), (C.c_int64 * 3)()
+        capi.check(self._lib.vosprop_timing_read(self._h, tot, cnt))
+        return {k: (tot[i], cnt[i]) for i, k in enumerate(('append', 'affinity', 'merge'))}
+
     # ------------------------------------------------------------------ per-video state
     def reset(self, H_d: int, W_d: int, H: int, W: int, d: int):
         capi.check(self._lib.vosprop_reset(self._h, H_d, W_d, H, W, d, self._stream()))

@@ -1,0 +1,99 @@
+"""ClipSegmenter: the library-level public call -- frames + first-frame annotation in, masks out.
+
+End-to-end path of one clip on one GPU:
+  pinned host frames --H2D (copy stream, batch ahead)--> VOSNet on cuDNN (fp16 autocast, as the
+  reference does on CUDA: inference_utils.py:35,52; channels_last) --> per frame: ring append +
+  fused propagation (libvosprop) --> uint8 masks accumulate on the device --> one D2H per clip.
+Feature extraction does not depend on propagation state, so frames go through
+the backbone in batches while propagation stays strictly sequential.  No host sync inside a clip.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _capi as capi
+from .engine import PropagationEngine, required_ring_slots
+from .sequence import start_sequence
+
+
+class ClipSegmenter:
+    def __init__(self, model: torch.nn.Module, device=None, sigma_1: float = 8.0, sigma_2: float = 21.0,
+                 frame_range: int = 40, ref_num: int = 9, temperature: float = 1.0,
+                 probability_propagation: bool = False, backbone_batch: int = 10, amp: bool = True,
+                 channels_last: bool = True, kernel: int = capi.KERNEL_TC):
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.model = model.to(self.device).eval()
+        if channels_last:
+            self.model = self.model.to(memory_format=torch.channels_last)
+        self.channels_last = channels_last
+        self.amp = amp
+        self.params = dict(sigma_1=sigma_1, sigma_2=sigma_2, frame_range=frame_range, ref_num=ref_num,
+                           temperature=temperature, probability_propagation=probability_propagation)
+        self.backbone_batch = backbone_batch
+        self.kernel = kernel
+        self.engine: Optional[PropagationEngine] = None
+        self.copy_stream = torch.cuda.Stream(self.device)
+
+    def _ensure_engine(self, n_pixels: int):
+        slots = max(required_ring_slots(self.params['frame_range'], self.params['ref_num']), 48)
+        if self.engine is None or self.engine.max_pixels < n_pixels or self.engine.ring_slots < slots:
+            if self.engine is not None:
+                self.engine.close()
+            self.engine = PropagationEngine(max_pixels=n_pixels, ring_slots=slots, device=self.device)
+
+    @torch.no_grad()
+    def embed(self, frames: torch.Tensor) -> torch.Tensor:
+        x = frames.contiguous(memory_format=torch.channels_last) if self.channels_last else frames
+        with torch.autocast('cuda', dtype=torch.float16, enabled=self.amp):
+            return self.model(x)
+
+    @torch.no_grad()
+    def segment(self, frames: torch.Tensor, first_label: torch.Tensor, out: Optional[torch.Tensor] = None,
+                sync: bool = True) -> torch.Tensor:
+        """frames (T,3,H,W) fp32, pinned host or device; first_label (H,W) integer class map.
+        Returns masks for frames 1..T-1 as (T-1,H,W) uint8 in pinned host memory."""
+        T, _, H, W = frames.shape
+        main = torch.cuda.current_stream(self.device)
+        B = self.backbone_batch
+        on_host = not frames.is_cuda
+        staged = {}
+
+        def stage(b0):
+            if not on_host:
+                return frames[b0:b0 + B]
+            with torch.cuda.stream(self.copy_stream):
+                dev = frames[b0:b0 + B].to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+            staged[b0] = ev
+            return dev
+
+        masks_dev = torch.empty((T - 1, H, W), dtype=torch.uint8, device=self.device)
+        nxt = stage(0)
+        p = self.params
+        for b0 in range(0, T, B):
+            cur = nxt
+            if b0 + B < T:
+                nxt = stage(b0 + B)          # copy of the next batch overlaps this batch's compute
+            if on_host:
+                main.wait_event(staged.pop(b0))
+                cur.record_stream(main)
+            feats = self.embed(cur)
+            for i in range(feats.shape[0]):
+                t = b0 + i
+                if t == 0:
+                    self._ensure_engine(feats.shape[2] * feats.shape[3])
+                    start_sequence(self.engine, feats[0], first_label.to(self.device, non_blocking=True))
+                    continue
+                self.engine.append(t, feats[i])
+                self.engine.step(t, p['frame_range'], p['ref_num'], p['sigma_1'], p['sigma_2'], p['temperature'],
+                                 p['probability_propagation'], kernel=self.kernel, want_prediction=False,
+                                 want_lowres=False, want_fullres=False, out_fullres=masks_dev[t - 1])
+        if out is None:
+            out = torch.empty((T - 1, H, W), dtype=torch.uint8, pin_memory=True)
+        out.copy_(masks_dev, non_blocking=True)
+        if sync:
+            main.synchronize()
+        return out
