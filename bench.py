@@ -71,24 +71,44 @@ def workload_config(args, n_gpus):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """SM clock, power and throttle reasons sampled DURING the timed region (NVML, ~10 ms period;
+    falls back to the nvidia-smi query of B200_PROFILING.md when NVML is unavailable)."""
+    REASONS = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4}
 
     def __init__(self, index):
-        self.index, self.rows, self._stop, self._th = index, [], threading.Event(), None
+        self.index, self.sm, self.power, self.mask, self.max_sm = index, [], [], 0, None
+        self._stop, self._th = threading.Event(), None
+
+    def _physical_index(self):
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        if vis:
+            ids = [v for v in vis.split(',') if v.strip()]
+            if self.index < len(ids) and ids[self.index].strip().isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.FIELDS}',
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(',')]
-                if len(parts) == 6:
-                    self.rows.append(parts)
-            except Exception:  # noqa: BLE001
-                pass
-            self._stop.wait(0.2)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self._stop.is_set():
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self._stop.wait(0.01)
+        except Exception:  # noqa: BLE001
+            fields = 'clocks.sm,clocks.max.sm,power.draw'
+            while not self._stop.is_set():
+                try:
+                    out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={fields}',
+                                          '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                    a, b, c = [float(x) for x in out.strip().split(',')]
+                    self.sm.append(a); self.max_sm = b; self.power.append(c)
+                except Exception:  # noqa: BLE001
+                    pass
+                self._stop.wait(0.1)
 
     def __enter__(self):
         self._th = threading.Thread(target=self._run, daemon=True)
@@ -100,13 +120,11 @@ class ClockSampler:
         self._th.join(timeout=6)
 
     def summary(self):
-        if not self.rows:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unsampled']}
-        sm = [float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit()]
-        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith('active') for r in self.rows)]
-        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': float(self.rows[0][1]),
-                'reasons': reasons, 'samples': len(self.rows)}
+        if not self.sm:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_sm, 'reasons': ['unsampled']}
+        return {'sm_mhz': statistics.median(self.sm), 'sm_min_mhz': min(self.sm), 'sm_max_mhz': self.max_sm,
+                'power_w_median': statistics.median(self.power) if self.power else None,
+                'reasons': [n for n, bit in self.REASONS.items() if self.mask & bit], 'samples': len(self.sm)}
 
 
 def measured_peaks():

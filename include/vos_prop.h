@@ -37,8 +37,12 @@ enum vosprop_dtype { VOSPROP_F32 = 0, VOSPROP_F16 = 1, VOSPROP_BF16 = 2 };
 /* memory order of a feature map handed to vosprop_append_features */
 enum vosprop_layout { VOSPROP_NCHW = 0 /* (K, H_d*W_d), torch default */, VOSPROP_NHWC = 1 /* (H_d*W_d, K) */ };
 enum vosprop_kernel {
-    VOSPROP_KERNEL_TC = 0,   /* product path: TMA + tcgen05 bf16x3 fused affinity kernel        */
-    VOSPROP_KERNEL_SIMT = 1  /* on-device fp32 checker (CUDA cores), same data path; tests only */
+    VOSPROP_KERNEL_TC = 0,   /* product path: TMA + tcgen05 bf16x3 fused affinity kernel; picks the
+                                index-label variant (target tile in TMEM, analytic prior, class bytes)
+                                when every reference carries index labels and W_d >= 32, else the
+                                general variant                                                  */
+    VOSPROP_KERNEL_SIMT = 1, /* on-device fp32 checker (CUDA cores), same data path; tests only */
+    VOSPROP_KERNEL_TC_DENSE = 2 /* force the general tensor-core variant (dense label records)  */
 };
 
 typedef struct vosprop_engine vosprop_engine;

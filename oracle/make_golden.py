@@ -44,6 +44,13 @@ SEQUENCES = {
     'E_many_objects': dict(T=12, H=72, W=120, n_objects=9, seed=15, feat_scale=0.30,
                            ref_num=9, frame_range=40, sigma_1=8.0, sigma_2=21.0,
                            temperature=1.0, probability_propagation=False),
+    # W_d >= 32: exercised by the index-label tensor-core kernel (vos_affinity_idx)
+    'F_wide_r9': dict(T=20, H=128, W=288, n_objects=3, seed=16, feat_scale=0.30,
+                      ref_num=9, frame_range=40, sigma_1=8.0, sigma_2=21.0, temperature=1.0,
+                      probability_propagation=False),
+    'G_wide_odd_r5': dict(T=24, H=200, W=264, n_objects=5, seed=17, feat_scale=0.30,
+                          ref_num=5, frame_range=10, sigma_1=6.0, sigma_2=15.0, temperature=1.3,
+                          probability_propagation=False),
 }
 GEN_KEYS = ('T', 'H', 'W', 'n_objects', 'seed', 'feat_scale')
 

@@ -56,8 +56,10 @@ struct AffinityParams {
     float scale2;         // temperature * log2(e)
     const float* meta;    // [slots * p_pad][16]
     float* partials;      // [grid * max_segs * 2][kPartFloats]
-    const __nv_bfloat16* ring_hi;  // used by the SIMT checker only
+    const __nv_bfloat16* ring_hi;  // read directly by the SIMT checker and by vos_affinity_idx's TMEM staging
     const __nv_bfloat16* ring_lo;
+    const uint8_t* cls;   // [slots * p_pad] class id per reference pixel (0xFF = padding), index-label mode
+    float inv_w;          // 1 / W_d
 };
 
 // -------------------------------------------------------------------------------------------
@@ -195,96 +197,101 @@ vos_affinity_tc(const __grid_constant__ CUtensorMap tmap_hi, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================= TMA producer: target tile per segment, 8 reference chunks per tile
-        if (lane == 0) {
-            vosd::SegIter it(dec, blockIdx.x);
-            int m_tile, n0, n1;
-            uint32_t stage = 0, phase = 0;
-            while (it.next(m_tile, n0, n1)) {
-                if (it.seg > 0) mbar_wait(q_empty, (it.seg - 1) & 1);
+        // ================= TMA producer: target tile per segment, 8 reference chunks per tile.
+        // Whole warp in the (uniform) control flow, elect.sync picks the issuing lane.
+        vosd::SegIter it(dec, blockIdx.x);
+        int m_tile, n0, n1;
+        uint32_t stage = 0, phase = 0;
+        while (it.next(m_tile, n0, n1)) {
+            if (it.seg > 0) mbar_wait(q_empty, (it.seg - 1) & 1);
+            const int q_row = prm.q_slot * prm.p_pad + m_tile * kTile;
+            if (elect_one()) {
                 mbar_arrive_expect_tx(q_full, kQBytes);
-                const int q_row = prm.q_slot * prm.p_pad + m_tile * kTile;
                 for (int kc = 0; kc < kNKC; ++kc) {
                     tma_load_2d(q_smem + kc * kChunkBytes, &tmap_hi, kc * kKC, q_row, q_full);
                     tma_load_2d(q_smem + (kNKC + kc) * kChunkBytes, &tmap_lo, kc * kKC, q_row, q_full);
                 }
-                for (int nt = n0; nt < n1; ++nt) {
-                    const int r = nt / dec.tpf;
-                    const int row0 = prm.ref_slot[r] * prm.p_pad + (nt - r * dec.tpf) * kTile;
-                    for (int c = 0; c < 2 * kNKC; ++c) {
-                        mbar_wait(&empty[stage], phase ^ 1);
+            }
+            __syncwarp();
+            for (int nt = n0; nt < n1; ++nt) {
+                const int r = nt / dec.tpf;
+                const int row0 = prm.ref_slot[r] * prm.p_pad + (nt - r * dec.tpf) * kTile;
+                for (int c = 0; c < 2 * kNKC; ++c) {
+                    mbar_wait_relaxed(&empty[stage], phase ^ 1, 64);
+                    if (elect_one()) {
                         mbar_arrive_expect_tx(&full[stage], kChunkBytes);
                         tma_load_2d(r_smem + stage * kChunkBytes, (c & 1) ? &tmap_lo : &tmap_hi, (c >> 1) * kKC,
                                     row0, &full[stage]);
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (single thread)
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16_f32(kTile, kTile);
-            vosd::SegIter it(dec, blockIdx.x);
-            int m_tile, n0, n1;
-            uint32_t stage = 0, phase = 0, tile_count = 0;
-            const uint32_t q_base = smem_u32(q_smem);
-            while (it.next(m_tile, n0, n1)) {
-                mbar_wait(q_full, it.seg & 1);
+        // ================= MMA issuer (one elected lane issues; SS form: A and B from shared memory)
+        constexpr uint32_t idesc = umma_idesc_bf16_f32(kTile, kTile);
+        vosd::SegIter it(dec, blockIdx.x);
+        int m_tile, n0, n1;
+        uint32_t stage = 0, phase = 0, tile_count = 0;
+        const uint64_t q_desc0 = umma_desc_kmajor_sw128(smem_u32(q_smem));
+        const uint64_t r_desc0 = umma_desc_kmajor_sw128(smem_u32(r_smem));
+        while (it.next(m_tile, n0, n1)) {
+            mbar_wait(q_full, it.seg & 1);
+            tc_fence_after_sync();
+            for (int nt = n0; nt < n1; ++nt, ++tile_count) {
+                const uint32_t buf = tile_count % kAccBufs;
+                const uint32_t aphase = (tile_count / kAccBufs) & 1;
+                mbar_wait_relaxed(&acc_empty[buf], aphase ^ 1, 32);
                 tc_fence_after_sync();
-                for (int nt = n0; nt < n1; ++nt, ++tile_count) {
-                    const uint32_t buf = tile_count % kAccBufs;
-                    const uint32_t aphase = (tile_count / kAccBufs) & 1;
-                    mbar_wait(&acc_empty[buf], aphase ^ 1);
+                const uint32_t d_tmem = tmem_base + buf * kTile;
+#pragma unroll
+                for (int c = 0; c < 2 * kNKC; ++c) {
+                    const int kc = c >> 1;
+                    mbar_wait(&full[stage], phase);
                     tc_fence_after_sync();
-                    const uint32_t d_tmem = tmem_base + buf * kTile;
-                    for (int c = 0; c < 2 * kNKC; ++c) {
-                        const int kc = c >> 1;
-                        mbar_wait(&full[stage], phase);
-                        tc_fence_after_sync();
-                        const uint32_t b_base = smem_u32(r_smem + stage * kChunkBytes);
-                        const uint32_t a_hi = q_base + kc * kChunkBytes;
-                        const uint32_t a_lo = q_base + (kNKC + kc) * kChunkBytes;
+                    if (elect_one()) {
+                        // descriptors advance in the (addr >> 4) field: 16 KiB chunk = +1024, K-step = +2
+                        const uint64_t b_desc = r_desc0 + static_cast<uint64_t>(stage * (kChunkBytes >> 4));
+                        const uint64_t a_hi = q_desc0 + static_cast<uint64_t>(kc * (kChunkBytes >> 4));
+                        const uint64_t a_lo = q_desc0 + static_cast<uint64_t>((kNKC + kc) * (kChunkBytes >> 4));
                         if ((c & 1) == 0) {   // reference hi chunk: Qhi.Rhi + Qlo.Rhi
 #pragma unroll
-                            for (int k = 0; k < kKC / 16; ++k)
-                                umma_bf16_ss(d_tmem, umma_desc_kmajor_sw128(a_hi + k * 32),
-                                             umma_desc_kmajor_sw128(b_base + k * 32), idesc, (c | k) != 0);
+                            for (int k = 0; k < kKC / 16; ++k) umma_bf16_ss(d_tmem, a_hi + 2 * k, b_desc + 2 * k, idesc, (c | k) != 0);
 #pragma unroll
-                            for (int k = 0; k < kKC / 16; ++k)
-                                umma_bf16_ss(d_tmem, umma_desc_kmajor_sw128(a_lo + k * 32),
-                                             umma_desc_kmajor_sw128(b_base + k * 32), idesc, 1);
+                            for (int k = 0; k < kKC / 16; ++k) umma_bf16_ss(d_tmem, a_lo + 2 * k, b_desc + 2 * k, idesc, 1);
                         } else {              // reference lo chunk: Qhi.Rlo
 #pragma unroll
-                            for (int k = 0; k < kKC / 16; ++k)
-                                umma_bf16_ss(d_tmem, umma_desc_kmajor_sw128(a_hi + k * 32),
-                                             umma_desc_kmajor_sw128(b_base + k * 32), idesc, 1);
+                            for (int k = 0; k < kKC / 16; ++k) umma_bf16_ss(d_tmem, a_hi + 2 * k, b_desc + 2 * k, idesc, 1);
                         }
-                        umma_commit(&empty[stage]);          // smem stage free once these MMAs retire
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        umma_commit(&empty[stage]);                       // smem stage free once these MMAs retire
+                        if (c == 2 * kNKC - 1) umma_commit(&acc_full[buf]);  // accumulator complete -> epilogue
                     }
-                    umma_commit(&acc_full[buf]);             // accumulator complete -> epilogue
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(q_empty);                        // target tile may be overwritten
             }
+            if (elect_one()) umma_commit(q_empty);                        // target tile may be overwritten
+            __syncwarp();
         }
     } else if (warp == 2) {
         // ================= meta producer: per reference tile 128 x {rowf, xf, V[14]} via 1-D bulk copy
-        if (lane == 0) {
-            vosd::SegIter it(dec, blockIdx.x);
-            int m_tile, n0, n1;
-            uint32_t count = 0;
-            while (it.next(m_tile, n0, n1)) {
-                for (int nt = n0; nt < n1; ++nt, ++count) {
-                    const uint32_t ms = count % kMetaStages;
-                    const uint32_t mph = (count / kMetaStages) & 1;
-                    const int r = nt / dec.tpf;
-                    const size_t row0 = static_cast<size_t>(prm.ref_slot[r]) * prm.p_pad + (nt - r * dec.tpf) * kTile;
-                    mbar_wait(&meta_empty[ms], mph ^ 1);
+        vosd::SegIter it(dec, blockIdx.x);
+        int m_tile, n0, n1;
+        uint32_t count = 0;
+        while (it.next(m_tile, n0, n1)) {
+            for (int nt = n0; nt < n1; ++nt, ++count) {
+                const uint32_t ms = count % kMetaStages;
+                const uint32_t mph = (count / kMetaStages) & 1;
+                const int r = nt / dec.tpf;
+                const size_t row0 = static_cast<size_t>(prm.ref_slot[r]) * prm.p_pad + (nt - r * dec.tpf) * kTile;
+                mbar_wait_relaxed(&meta_empty[ms], mph ^ 1, 128);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&meta_full[ms], kMetaTileBytes);
                     bulk_load_1d(meta_smem + ms * (kMetaTileBytes / 16), prm.meta + row0 * kMetaFloats,
                                  kMetaTileBytes, &meta_full[ms]);
                 }
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {
@@ -438,6 +445,7 @@ struct MergeParams {
     int32_t write_labels, probability;
     const float* partials;
     float* meta;
+    uint8_t* cls;              // class-id ring (index-label mode of the next steps)
     float* out_prediction;     // (d, P) or null
     uint8_t* out_mask_lowres;  // (P) or null
     uint8_t* out_mask_fullres; // (H, W) or null
@@ -494,6 +502,7 @@ __global__ void __launch_bounds__(128) vos_merge_writeback(const MergeParams prm
 #pragma unroll
             for (int k = 0; k < kMaxClasses; ++k)
                 mrec[k] = (k < prm.d) ? (prm.probability ? acc[k] : (k == best ? 1.f : 0.f)) : 0.f;
+            prm.cls[static_cast<size_t>(prm.q_slot) * prm.p_pad + pix] = static_cast<uint8_t>(best);
         }
         if (prm.out_mask_lowres) prm.out_mask_lowres[pix] = static_cast<uint8_t>(best);
         row_cls[x] = static_cast<uint8_t>(best);
@@ -570,10 +579,12 @@ __global__ void vos_init_meta(float* __restrict__ meta, int slots, int p_pad, in
     rec[1] = rec[2] = rec[3] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-__global__ void vos_set_labels_index(float* __restrict__ meta_slot, const uint8_t* __restrict__ cls, int n_pixels) {
+__global__ void vos_set_labels_index(float* __restrict__ meta_slot, uint8_t* __restrict__ cls_slot,
+                                     const uint8_t* __restrict__ cls, int n_pixels) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pixels) return;
     const int c = cls[p];
+    cls_slot[p] = static_cast<uint8_t>(c);
     float* rec = meta_slot + static_cast<size_t>(p) * kMetaFloats + 2;
 #pragma unroll
     for (int k = 0; k < kMaxClasses; ++k) rec[k] = (k == c) ? 1.f : 0.f;

@@ -15,6 +15,7 @@
 
 #include "decompose.h"
 #include "kernels.cuh"
+#include "affinity_idx.cuh"
 
 namespace {
 
@@ -50,12 +51,13 @@ struct vosprop_engine {
     __nv_bfloat16* ring_hi = nullptr;
     __nv_bfloat16* ring_lo = nullptr;
     float* meta = nullptr;
+    uint8_t* cls = nullptr;   // class-id ring, [slots * p_pad]
     float* partials = nullptr;
     size_t partial_records = 0;
     CUtensorMap tmap_hi{}, tmap_lo{};
     EncodeTiledFn encode = nullptr;
     std::vector<int> slot_frame;
-    std::vector<char> slot_labels;
+    std::vector<char> slot_labels;   // 0: none, 1: index labels (cls ring + one-hot record), 2: dense record only
     int64_t launches = 0;
     // optional per-kernel timing (bench.py roofline)
     std::vector<cudaEvent_t> ev;      // 2 events per timed launch
@@ -102,6 +104,9 @@ int encode_maps(vosprop_engine* e) {
 template <int D>
 int launch_affinity(vosprop_engine* e, const vosk::AffinityParams& prm, int grid, int kernel, cudaStream_t st) {
     if (kernel == VOSPROP_KERNEL_TC) {
+        VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_idx<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kIdxSmem));
+        vosk::vos_affinity_idx<D><<<grid, vosk::kIdxThreads, vosk::kIdxSmem, st>>>(e->tmap_hi, e->tmap_lo, prm);
+    } else if (kernel == VOSPROP_KERNEL_TC_DENSE) {
         VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kSmemTc));
         vosk::vos_affinity_tc<D><<<grid, vosk::kTcThreads, vosk::kSmemTc, st>>>(e->tmap_hi, e->tmap_lo, prm);
     } else {
@@ -178,7 +183,8 @@ int vosprop_create(const vosprop_config* cfg, vosprop_engine** out) {
     cudaError_t a2 = cudaMalloc(&e->ring_lo, rows * vosk::kK * 2);
     cudaError_t a3 = cudaMalloc(&e->meta, rows * vosk::kMetaFloats * 4);
     cudaError_t a4 = cudaMalloc(&e->partials, e->partial_records * vosk::kPartFloats * 4);
-    if (a1 != cudaSuccess || a2 != cudaSuccess || a3 != cudaSuccess || a4 != cudaSuccess) {
+    cudaError_t a5 = cudaMalloc(&e->cls, rows);
+    if (a1 != cudaSuccess || a2 != cudaSuccess || a3 != cudaSuccess || a4 != cudaSuccess || a5 != cudaSuccess) {
         vosprop_destroy(e);
         return fail(VOSPROP_ERR_CUDA, "cudaMalloc of the reference-memory ring failed (%zu rows)", rows);
     }
@@ -201,6 +207,7 @@ void vosprop_destroy(vosprop_engine* e) {
     cudaFree(e->ring_lo);
     cudaFree(e->meta);
     cudaFree(e->partials);
+    cudaFree(e->cls);
     for (cudaEvent_t ev : e->ev) cudaEventDestroy(ev);
     delete e;
 }
@@ -223,6 +230,7 @@ int vosprop_reset(vosprop_engine* e, int32_t H_d, int32_t W_d, int32_t H, int32_
     const size_t n = static_cast<size_t>(e->cfg.ring_slots) * e->p_pad;
     vosk::vos_init_meta<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(e->meta, e->cfg.ring_slots, e->p_pad, e->P, W_d);
     VOS_CUDA(cudaGetLastError());
+    VOS_CUDA(cudaMemsetAsync(e->cls, 0xFF, n, st));   // padding pixels keep class 0xFF
     e->launches++;
     return VOSPROP_OK;
 }
@@ -259,23 +267,24 @@ int vosprop_append_features(vosprop_engine* e, int32_t frame_idx, const void* fe
     return VOSPROP_OK;
 }
 
-static int labels_target(vosprop_engine* e, int frame_idx, float** meta_slot) {
+static int labels_target(vosprop_engine* e, int frame_idx, float** meta_slot, int kind) {
     int rc = check_frame(e, frame_idx);
     if (rc) return rc;
     const int slot = frame_idx % e->cfg.ring_slots;
     if (e->slot_frame[slot] != frame_idx)
         return fail(VOSPROP_ERR_STATE, "frame %d is not in the ring (slot %d holds %d): append its features first", frame_idx, slot, e->slot_frame[slot]);
     *meta_slot = e->meta + static_cast<size_t>(slot) * e->p_pad * vosk::kMetaFloats;
-    e->slot_labels[slot] = 1;
+    e->slot_labels[slot] = static_cast<char>(kind);
     return VOSPROP_OK;
 }
 
 int vosprop_set_labels_index(vosprop_engine* e, int32_t frame_idx, const uint8_t* class_idx, void* stream) {
     float* ms = nullptr;
-    int rc = labels_target(e, frame_idx, &ms);
+    int rc = labels_target(e, frame_idx, &ms, 1);
     if (rc) return rc;
     if (!class_idx) return fail(VOSPROP_ERR_INVALID, "null class_idx");
-    vosk::vos_set_labels_index<<<(e->P + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(ms, class_idx, e->P);
+    uint8_t* cls_slot = e->cls + static_cast<size_t>(frame_idx % e->cfg.ring_slots) * e->p_pad;
+    vosk::vos_set_labels_index<<<(e->P + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(ms, cls_slot, class_idx, e->P);
     VOS_CUDA(cudaGetLastError());
     e->launches++;
     return VOSPROP_OK;
@@ -283,7 +292,7 @@ int vosprop_set_labels_index(vosprop_engine* e, int32_t frame_idx, const uint8_t
 
 int vosprop_set_labels_dense(vosprop_engine* e, int32_t frame_idx, const float* labels, void* stream) {
     float* ms = nullptr;
-    int rc = labels_target(e, frame_idx, &ms);
+    int rc = labels_target(e, frame_idx, &ms, 2);
     if (rc) return rc;
     if (!labels) return fail(VOSPROP_ERR_INVALID, "null labels");
     vosk::vos_set_labels_dense<<<(e->P + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(ms, labels, e->P, e->d);
@@ -300,7 +309,7 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     if (!(s->temperature >= 0.f) || !std::isfinite(s->temperature))
         return fail(VOSPROP_ERR_UNSUPPORTED, "temperature %g: only finite temperature >= 0 is supported", (double)s->temperature);
     if (s->topk != 0) return fail(VOSPROP_ERR_UNSUPPORTED, "top-k mode is not built yet (topk=%d)", s->topk);
-    if (s->kernel != VOSPROP_KERNEL_TC && s->kernel != VOSPROP_KERNEL_SIMT) return fail(VOSPROP_ERR_INVALID, "unknown kernel %d", s->kernel);
+    if (s->kernel < VOSPROP_KERNEL_TC || s->kernel > VOSPROP_KERNEL_TC_DENSE) return fail(VOSPROP_ERR_INVALID, "unknown kernel %d", s->kernel);
     if (s->out_mask_fullres && static_cast<int64_t>(e->H) * e->W > e->cfg.max_fullres_pixels && e->cfg.max_fullres_pixels > 0)
         return fail(VOSPROP_ERR_UNSUPPORTED, "full-resolution frame larger than configured");
     const int S = e->cfg.ring_slots;
@@ -308,6 +317,7 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     if (e->slot_frame[q_slot] != s->frame_idx)
         return fail(VOSPROP_ERR_STATE, "target frame %d is not in the ring: append its features first", s->frame_idx);
 
+    bool all_index = true;
     vosk::AffinityParams ap{};
     ap.n_pixels = e->P; ap.p_pad = e->p_pad; ap.w_lowres = e->W_d; ap.n_refs = s->n_refs; ap.q_slot = q_slot;
     ap.num_sms = e->num_sms;
@@ -321,18 +331,24 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
         if (slot == q_slot && s->write_labels)
             return fail(VOSPROP_ERR_STATE, "reference frame %d aliases the target's ring slot", f);
         ap.ref_slot[r] = slot;
+        all_index = all_index && e->slot_labels[slot] == 1;
         const float sg = s->ref_sigma[r];
         ap.ref_coef[r] = sg > 0.f ? static_cast<float>(1.4426950408889634 / (static_cast<double>(sg) * sg)) : 0.f;
     }
     ap.scale2 = static_cast<float>(static_cast<double>(s->temperature) * 1.4426950408889634);
     ap.meta = e->meta; ap.partials = e->partials; ap.ring_hi = e->ring_hi; ap.ring_lo = e->ring_lo;
+    ap.cls = e->cls; ap.inv_w = 1.0f / static_cast<float>(e->W_d);
+    // the index-label kernel needs one class byte per reference pixel and W_d >= 32; anything else
+    // (dense / probability labels, tiny maps) runs on the general tensor-core kernel
+    int kernel = s->kernel;
+    if (kernel == VOSPROP_KERNEL_TC && (!all_index || e->W_d < 32)) kernel = VOSPROP_KERNEL_TC_DENSE;
     const vosd::Decomp dec = vosd::make_decomp(e->P, s->n_refs, e->num_sms);
     if (static_cast<size_t>(dec.grid) * dec.max_segs * 2 > e->partial_records)
         return fail(VOSPROP_ERR_UNSUPPORTED, "partial buffer too small (grid %d x segs %d)", dec.grid, dec.max_segs);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     {
         TimedLaunch timed(e, VOSPROP_T_AFFINITY, st);
-        rc = dispatch_affinity(e, ap, dec.grid, s->kernel, st);
+        rc = dispatch_affinity(e, ap, dec.grid, kernel, st);
     }
     if (rc) return rc;
 
@@ -340,14 +356,14 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     mp.n_pixels = e->P; mp.p_pad = e->p_pad; mp.w_lowres = e->W_d; mp.h_lowres = e->H_d; mp.n_refs = s->n_refs;
     mp.num_sms = e->num_sms; mp.d = e->d; mp.H = e->H; mp.W = e->W; mp.q_slot = q_slot;
     mp.write_labels = s->write_labels; mp.probability = s->probability_propagation;
-    mp.partials = e->partials; mp.meta = e->meta;
+    mp.partials = e->partials; mp.meta = e->meta; mp.cls = e->cls;
     mp.out_prediction = s->out_prediction; mp.out_mask_lowres = s->out_mask_lowres; mp.out_mask_fullres = s->out_mask_fullres;
     {
         TimedLaunch timed(e, VOSPROP_T_MERGE, st);
         vosk::vos_merge_writeback<<<e->H_d, 128, e->W_d, st>>>(mp);
     }
     VOS_CUDA(cudaGetLastError());
-    if (s->write_labels) e->slot_labels[q_slot] = 1;
+    if (s->write_labels) e->slot_labels[q_slot] = s->probability_propagation ? 2 : 1;
     e->launches += 2;
     return VOSPROP_OK;
 }

@@ -9,7 +9,7 @@ MAX_CLASSES = 14
 FEAT_DIM = 256
 F32, F16, BF16 = 0, 1, 2
 NCHW, NHWC = 0, 1
-KERNEL_TC, KERNEL_SIMT = 0, 1
+KERNEL_TC, KERNEL_SIMT, KERNEL_TC_DENSE = 0, 1, 2
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4
 
 LIB_PATH = Path(__file__).resolve().parent.parent / 'csrc' / 'libvosprop.so'

@@ -11,7 +11,7 @@ from oracle import propagation_oracle as O
 GOLDEN = Path(__file__).resolve().parent / 'golden'
 META = json.loads((GOLDEN / 'meta.json').read_text())
 GEN_KEYS = ('T', 'H', 'W', 'n_objects', 'seed', 'feat_scale')
-SEQ_NAMES = [k for k in META if k[0] in 'ABCDE' and k[1] == '_']
+SEQ_NAMES = [k for k in META if k[0] in 'ABCDEFG' and k[1] == '_']
 
 
 def sha(t):
