@@ -21,31 +21,25 @@
 
 namespace vosk {
 
-constexpr int kIdxThreads = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int kIdxEpiWarps = 16;     // 4 per scheduler: each owns 32 TMEM lanes x 32 logit columns of a tile
+constexpr int kIdxEpiThreads = kIdxEpiWarps * 32;
+constexpr int kIdxThreads = 64 + kIdxEpiThreads;   // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue
+constexpr int kIdxSub = 4;           // partial records per (CTA, segment): one per 32-column quarter
 constexpr int kIdxStages = 13;       // 13 x 16 KiB reference chunks in flight
 constexpr int kIdxAccBufs = 2;       // TMEM: [0,256) two accumulators, [256,384) Q hi, [384,512) Q lo
 constexpr int kIdxSmem = kIdxStages * kChunkBytes + 512 + 1024;
 constexpr uint32_t kTmemQ = 256;
 
 struct ChunkGeom {
-    float aA, bA, aB, bB;   // alpha/beta before (A) and after (B) the row wrap
-    int jw;                 // first column of the chunk that belongs to the next image row (>= 32: none)
+    float drc;   // (n_c - m) / W : row-coordinate difference of the step's first column (fractional rows)
+    float bx;    // x(n_c) - x(m)  : column difference of the step's first column
+    int jw;      // first column of the step that belongs to the next image row (>= kQC: none)
 };
 
-// geometry of the 32-column chunk whose first reference pixel is n_c (index inside its frame),
-// for target pixel m with column xm;  xc = n_c mod W
-__device__ __forceinline__ ChunkGeom chunk_geom(int n_c, int xc, int m, int xm, int W, float inv_w, float coef) {
-    ChunkGeom g;
-    const float drc = static_cast<float>(n_c - m) * inv_w;
-    const float bxA = static_cast<float>(xc - xm);
-    const float bxB = bxA - static_cast<float>(W);
-    const float c2 = -2.f * coef;
-    g.aA = -coef * fmaf(bxA, bxA, drc * drc);
-    g.aB = -coef * fmaf(bxB, bxB, drc * drc);
-    g.bA = c2 * fmaf(drc, inv_w, bxA);
-    g.bB = c2 * fmaf(drc, inv_w, bxB);
-    g.jw = W - xc;
-    return g;
+// alpha + beta*j + gamma*j^2 = -coef*((drc + j/W)^2 + (bx + j)^2); `shift` is folded into alpha
+__device__ __forceinline__ void quad_coeffs(float drc, float bx, float inv_w, float coef, float shift, float& alpha, float& beta) {
+    alpha = fmaf(-coef, fmaf(bx, bx, drc * drc), shift);
+    beta = -2.f * coef * fmaf(drc, inv_w, bx);
 }
 
 template <int D>
@@ -69,13 +63,16 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, float (&v)[16
 
 constexpr int kQC = 16;   // columns per epilogue step (kept small: the three unrolled paths must fit the I-cache)
 
-// One 16-column step.  cls_bits: for class c, bit j of cmask[c] says column j carries class c (built from
-// the lanes' class bytes with ballots by the caller).  n_valid: valid leading columns (>= 16 unless ragged).
+// One 16-column step of one target pixel.  cls_lane: class byte of column (lane - lane_shift) for the 16
+// lanes [lane_shift, lane_shift+16).  n_valid: valid leading columns (>= 16 unless the tile is ragged).
+// Arithmetic per column j:  e = s*scale2 - m ;  l += 2^e ;  pw = 2^(e + alpha + beta*j + gamma*j^2) ;
+// acc[class(j)] += pw  -- in packed fp32 pairs (FFMA2/FADD2), the two exp2 per column on the MUFU.
 template <int D>
 __device__ __forceinline__ void consume16_idx(RowAcc<D>& st, float (&v)[kQC], uint32_t cls_lane, int lane_shift,
-                                              int n_valid, const ChunkGeom& g, float gamma, float scale2) {
+                                              int n_valid, const ChunkGeom& g, float inv_w, float coef, float gamma,
+                                              float scale2, float w_lowres) {
     const uint32_t full = 0xffffffffu;
-    const uint32_t window = 0xffffu << lane_shift;          // the 16 lanes holding this step's class bytes
+    const uint32_t window = 0xffffu << lane_shift;
     const bool partial = n_valid < kQC;
     const uint32_t valid = partial ? (n_valid <= 0 ? 0u : ((1u << n_valid) - 1u)) : 0xffffu;
     const uint32_t first = __shfl_sync(full, cls_lane, lane_shift);
@@ -97,48 +94,91 @@ __device__ __forceinline__ void consume16_idx(RowAcc<D>& st, float (&v)[kQC], ui
         st.m = m_new;
     }
     const float neg_m = -st.m;
-    if (homog) {
-        float sum = 0.f;
-        if (g.jw >= kQC) {   // path A: one class, no row wrap
+    const float2 s2 = make_float2(scale2, scale2);
+    const float2 nm2 = make_float2(neg_m, neg_m);
+    const float2 g2 = make_float2(gamma, gamma);
+    float aA, bA;
+    quad_coeffs(g.drc, g.bx, inv_w, coef, neg_m, aA, bA);      // alpha already contains -m
+    float2 l2 = make_float2(0.f, 0.f), sum2 = make_float2(0.f, 0.f);
+    if (homog && g.jw >= kQC) {
+        // ---- path A: one class, no row wrap.  t_j = alpha + beta*j + gamma*j^2 by forward differences on
+        // column pairs: T = (t_j, t_j+1), T += dT, dT += 8*gamma  (no per-column constants to materialise)
+        float2 T = make_float2(aA, aA + bA + gamma);
+        float2 dT = make_float2(2.f * bA + 4.f * gamma, 2.f * bA + 8.f * gamma);
+        const float2 c8 = make_float2(8.f * gamma, 8.f * gamma);
 #pragma unroll
-            for (int j = 0; j < kQC; ++j) {
-                const float e = fmaf(v[j], scale2, neg_m);
-                st.l += ex2(e);
-                float t = fmaf(g.bA, static_cast<float>(j), g.aA);
-                t = fmaf(gamma, static_cast<float>(j * j), t);
-                sum += ex2(e + t);
-            }
-        } else {             // path B: one class, columns >= jw sit on the next image row
-#pragma unroll
-            for (int j = 0; j < kQC; ++j) {
-                const float e = fmaf(v[j], scale2, neg_m);
-                st.l += ex2(e);
-                const bool w = j >= g.jw;
-                float t = fmaf(w ? g.bB : g.bA, static_cast<float>(j), w ? g.aB : g.aA);
-                t = fmaf(gamma, static_cast<float>(j * j), t);
-                sum += ex2(e + t);
-            }
+        for (int j = 0; j < kQC; j += 2) {
+            const float2 v2 = make_float2(v[j], v[j + 1]);
+            const float2 e2 = ffma2(v2, s2, nm2);
+            const float2 u2 = ffma2(v2, s2, T);
+            T = fadd2(T, dT);
+            dT = fadd2(dT, c8);
+            l2 = fadd2(l2, make_float2(ex2(e2.x), ex2(e2.y)));
+            sum2 = fadd2(sum2, make_float2(ex2(u2.x), ex2(u2.y)));
         }
-        add_to_class<D>(st, static_cast<int>(first), sum);
-    } else {                 // path C: mixed classes and/or ragged tile
-        uint32_t mask[D];
+        st.l += l2.x + l2.y;
+        add_to_class<D>(st, static_cast<int>(first), sum2.x + sum2.y);
+        return;
+    }
+    float aB, bB;
+    quad_coeffs(g.drc, g.bx - w_lowres, inv_w, coef, neg_m, aB, bB);   // columns >= jw: next image row
+    if (homog) {
+        // ---- path B: one class, row wrap inside the step
 #pragma unroll
-        for (int c = 0; c < D; ++c)
-            mask[c] = (__ballot_sync(full, cls_lane == static_cast<uint32_t>(c)) >> lane_shift) & valid;
+        for (int j = 0; j < kQC; j += 2) {
+            const bool w0 = j >= g.jw, w1 = j + 1 >= g.jw;
+            const float2 v2 = make_float2(v[j], v[j + 1]);
+            const float2 e2 = ffma2(v2, s2, nm2);
+            float2 t2 = ffma2(make_float2(w0 ? bB : bA, w1 ? bB : bA), make_float2(float(j), float(j + 1)),
+                              make_float2(w0 ? aB : aA, w1 ? aB : aA));
+            t2 = ffma2(g2, make_float2(float(j * j), float((j + 1) * (j + 1))), t2);
+            const float2 u2 = ffma2(v2, s2, t2);
+            l2 = fadd2(l2, make_float2(ex2(e2.x), ex2(e2.y)));
+            sum2 = fadd2(sum2, make_float2(ex2(u2.x), ex2(u2.y)));
+        }
+        st.l += l2.x + l2.y;
+        add_to_class<D>(st, static_cast<int>(first), sum2.x + sum2.y);
+        return;
+    }
+    // ---- path C: mixed classes and/or ragged tile.  Classes >= 1 get predicated adds; class 0 receives
+    // the remainder of the step total (exact up to one rounding of the total).
+    uint32_t mask[D];
+    float part[D];
 #pragma unroll
-        for (int j = 0; j < kQC; ++j) {
-            float e = fmaf(v[j], scale2, neg_m);
-            if (!((valid >> j) & 1u)) e = -INFINITY;
-            st.l += ex2(e);
-            const bool w = j >= g.jw;
-            float t = fmaf(w ? g.bB : g.bA, static_cast<float>(j), w ? g.aB : g.aA);
-            t = fmaf(gamma, static_cast<float>(j * j), t);
-            const float pw = ex2(e + t);
+    for (int c = 1; c < D; ++c) {
+        mask[c] = (__ballot_sync(full, cls_lane == static_cast<uint32_t>(c)) >> lane_shift) & valid;
+        part[c] = 0.f;
+    }
 #pragma unroll
-            for (int c = 0; c < D; ++c)
-                if ((mask[c] >> j) & 1u) st.acc[c] += pw;
+    for (int j = 0; j < kQC; j += 2) {
+        const bool w0 = j >= g.jw, w1 = j + 1 >= g.jw;
+        const float2 v2 = make_float2(v[j], v[j + 1]);
+        float2 e2 = ffma2(v2, s2, nm2);
+        float2 t2 = ffma2(make_float2(w0 ? bB : bA, w1 ? bB : bA), make_float2(float(j), float(j + 1)),
+                          make_float2(w0 ? aB : aA, w1 ? aB : aA));
+        t2 = ffma2(g2, make_float2(float(j * j), float((j + 1) * (j + 1))), t2);
+        float2 u2 = ffma2(v2, s2, t2);
+        if (partial) {   // padding columns: weight exactly 0 in both sums
+            if (!((valid >> j) & 1u)) { e2.x = -INFINITY; u2.x = -INFINITY; }
+            if (!((valid >> (j + 1)) & 1u)) { e2.y = -INFINITY; u2.y = -INFINITY; }
+        }
+        l2 = fadd2(l2, make_float2(ex2(e2.x), ex2(e2.y)));
+        const float pw0 = ex2(u2.x), pw1 = ex2(u2.y);
+        sum2 = fadd2(sum2, make_float2(pw0, pw1));
+#pragma unroll
+        for (int c = 1; c < D; ++c) {
+            if ((mask[c] >> j) & 1u) part[c] += pw0;
+            if ((mask[c] >> (j + 1)) & 1u) part[c] += pw1;
         }
     }
+    st.l += l2.x + l2.y;
+    float rest = sum2.x + sum2.y;
+#pragma unroll
+    for (int c = 1; c < D; ++c) {
+        st.acc[c] += part[c];
+        rest -= part[c];
+    }
+    st.acc[0] += fmaxf(rest, 0.f);
 }
 
 template <int D>
@@ -165,9 +205,9 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
         prefetch_tmap(&tmap_hi);
         prefetch_tmap(&tmap_lo);
         for (int i = 0; i < kIdxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(q_full, kEpiThreads);
+        mbar_init(q_full, kIdxEpiThreads);
         mbar_init(q_empty, 1);
-        for (int i = 0; i < kIdxAccBufs; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiThreads); }
+        for (int i = 0; i < kIdxAccBufs; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kIdxEpiThreads); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -247,9 +287,9 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             __syncwarp();
         }
     } else {
-        // ================= epilogue: warps 2-9; TMEM lanes [32*(warp%4), +32); columns [64*half, +64)
+        // ================= epilogue: warps 2-17; TMEM lanes [32*(warp%4), +32); logit columns [32*sub, +32)
         const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int sub = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
         const int W = prm.w_lowres;
@@ -257,24 +297,25 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
         int m_tile, n0, n1;
         uint32_t tile_count = 0;
         while (it.next(m_tile, n0, n1)) {
-            // ---- stage this segment's target tile into TMEM: half 0 writes hi, half 1 writes lo
+            // ---- stage this segment's target tile into TMEM: column quarters 0,1 write the two halves of
+            // Q hi (TMEM columns [256,384)), quarters 2,3 the two halves of Q lo ([384,512))
             if (it.seg > 0) {
                 mbar_wait(q_empty, (it.seg - 1) & 1);
                 tc_fence_after_sync();
             }
             {
-                const __nv_bfloat16* src = (half ? prm.ring_lo : prm.ring_hi) +
+                const __nv_bfloat16* src = ((sub & 2) ? prm.ring_lo : prm.ring_hi) +
                                            (static_cast<size_t>(prm.q_slot) * prm.p_pad + m_tile * kTile + row) * kK;
-                const uint4* src4 = reinterpret_cast<const uint4*>(src);
+                const uint4* src4 = reinterpret_cast<const uint4*>(src) + (sub & 1) * 16;
 #pragma unroll
-                for (int pass = 0; pass < 4; ++pass) {
+                for (int pass = 0; pass < 2; ++pass) {
                     uint32_t regs[32];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const uint4 q = __ldg(src4 + pass * 8 + i);
                         regs[4 * i] = q.x; regs[4 * i + 1] = q.y; regs[4 * i + 2] = q.z; regs[4 * i + 3] = q.w;
                     }
-                    tmem_st_32x32b_x32(tmem_base + lane_base + kTmemQ + half * 128 + pass * 32, regs);
+                    tmem_st_32x32b_x32(tmem_base + lane_base + kTmemQ + sub * 64 + pass * 32, regs);
                 }
                 tmem_st_wait();
                 tc_fence_before_sync();
@@ -287,33 +328,37 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             // (reference frame r, tile j inside it) of the segment's first tile; afterwards incremental
             int r = n0 / dec.tpf;
             int j = n0 - r * dec.tpf;
-            int x_half = (j * kTile + half * 64) % W;     // image column of this half's first pixel
+            int x_sub = (j * kTile + sub * 32) % W;       // image column of this warp's first logit column
             const int x_step = kTile % W;
             for (int nt = n0; nt < n1; ++nt, ++tile_count) {
                 const uint32_t buf = tile_count % kIdxAccBufs;
                 const uint32_t aphase = (tile_count / kIdxAccBufs) & 1;
-                const size_t row0 = static_cast<size_t>(prm.ref_slot[r]) * prm.p_pad + j * kTile + half * 64;
-                const uint32_t cls0 = prm.cls[row0 + lane];        // class bytes of columns [0,32) / [32,64)
-                const uint32_t cls1 = prm.cls[row0 + 32 + lane];
+                const size_t row0 = static_cast<size_t>(prm.ref_slot[r]) * prm.p_pad + j * kTile + sub * 32;
+                const uint32_t cls_lane = prm.cls[row0 + lane];      // class byte of logit column `lane`
                 const float coef = prm.ref_coef[r];
                 const float gamma = -coef * fmaf(prm.inv_w, prm.inv_w, 1.0f);
-                const int n_half = j * kTile + half * 64;           // pixel index (in its frame) of column 0
-                const int n_valid = min(kTile, prm.n_pixels - j * kTile) - half * 64;
+                const int n_sub = j * kTile + sub * 32;              // pixel index (in its frame) of column 0
+                const int n_valid = min(kTile, prm.n_pixels - j * kTile) - sub * 32;
                 mbar_wait(&acc_full[buf], aphase);
                 tc_fence_after_sync();
-                const uint32_t taddr = tmem_base + lane_base + buf * kTile + half * 64;
-                int xq = x_half;
+                const uint32_t taddr = tmem_base + lane_base + buf * kTile + sub * 32;
+                float v0[kQC], v1[kQC];
+                tmem_ld_32x32b_x16(taddr, v0);
+                tmem_ld_32x32b_x16(taddr + kQC, v1);
+                tmem_ld_wait();
+                tc_fence_before_sync();
+                mbar_arrive(&acc_empty[buf]);                        // this warp's columns are in registers
+                int xq = x_sub;
 #pragma unroll 1
-                for (int q = 0; q < 64 / kQC; ++q) {
-                    float v[kQC];
-                    tmem_ld_32x32b_x16(taddr + q * kQC, v);
-                    const ChunkGeom g = chunk_geom(n_half + q * kQC, xq, m, xm, W, prm.inv_w, coef);
-                    tmem_ld_wait();
-                    if (q == 64 / kQC - 1) {                        // accumulator fully drained into registers
-                        tc_fence_before_sync();
-                        mbar_arrive(&acc_empty[buf]);
-                    }
-                    consume16_idx<D>(st, v, (q & 2) ? cls1 : cls0, (q & 1) * kQC, n_valid - q * kQC, g, gamma, prm.scale2);
+                for (int q = 0; q < 2; ++q) {
+                    ChunkGeom g;
+                    g.drc = static_cast<float>(n_sub + q * kQC - m) * prm.inv_w;
+                    g.bx = static_cast<float>(xq - xm);
+                    g.jw = W - xq;
+                    if (q == 0)
+                        consume16_idx<D>(st, v0, cls_lane, 0, n_valid, g, prm.inv_w, coef, gamma, prm.scale2, static_cast<float>(W));
+                    else
+                        consume16_idx<D>(st, v1, cls_lane, kQC, n_valid - kQC, g, prm.inv_w, coef, gamma, prm.scale2, static_cast<float>(W));
                     xq += kQC;
                     if (xq >= W) xq -= W;
                 }
@@ -321,14 +366,14 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                 if (++j == dec.tpf) {
                     j = 0;
                     ++r;
-                    x_half = (half * 64) % W;
+                    x_sub = (sub * 32) % W;
                 } else {
-                    x_half += x_step;
-                    if (x_half >= W) x_half -= W;
+                    x_sub += x_step;
+                    if (x_sub >= W) x_sub -= W;
                 }
             }
             float* rec = prm.partials +
-                         (static_cast<size_t>(blockIdx.x * dec.max_segs + it.seg) * 2 + half) * kPartFloats;
+                         (static_cast<size_t>(blockIdx.x * dec.max_segs + it.seg) * kIdxSub + sub) * kPartFloats;
             store_partial<D>(st, rec, row);
         }
     }

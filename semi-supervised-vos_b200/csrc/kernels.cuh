@@ -443,6 +443,7 @@ struct MergeParams {
     int32_t H, W;              // full resolution
     int32_t q_slot;
     int32_t write_labels, probability;
+    int32_t n_sub;             // partial records per (CTA, segment): 2 (half tiles) or 4 (quarter tiles)
     const float* partials;
     float* meta;
     uint8_t* cls;              // class-id ring (index-label mode of the next steps)
@@ -468,16 +469,16 @@ __global__ void __launch_bounds__(128) vos_merge_writeback(const MergeParams prm
         float M = kNegBig;
         for (int c = c_first; c <= c_last; ++c) {
             const int seg = mt - static_cast<int>(vosd::cta_begin(dec, c) / dec.nt);
-            const float* rec = prm.partials + (static_cast<size_t>(c * dec.max_segs + seg) * 2) * kPartFloats;
-            M = fmaxf(M, fmaxf(rec[row], rec[kPartFloats + row]));
+            const float* rec = prm.partials + (static_cast<size_t>(c * dec.max_segs + seg) * prm.n_sub) * kPartFloats;
+            for (int h = 0; h < prm.n_sub; ++h) M = fmaxf(M, rec[h * kPartFloats + row]);
         }
         float L = 0.f, acc[kMaxClasses];
 #pragma unroll
         for (int k = 0; k < kMaxClasses; ++k) acc[k] = 0.f;
         for (int c = c_first; c <= c_last; ++c) {
             const int seg = mt - static_cast<int>(vosd::cta_begin(dec, c) / dec.nt);
-            for (int h = 0; h < 2; ++h) {
-                const float* rec = prm.partials + (static_cast<size_t>(c * dec.max_segs + seg) * 2 + h) * kPartFloats;
+            for (int h = 0; h < prm.n_sub; ++h) {
+                const float* rec = prm.partials + (static_cast<size_t>(c * dec.max_segs + seg) * prm.n_sub + h) * kPartFloats;
                 const float wgt = vosptx::ex2(rec[row] - M);
                 L = fmaf(rec[kTile + row], wgt, L);
 #pragma unroll

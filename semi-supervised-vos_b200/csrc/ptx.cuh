@@ -185,6 +185,21 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 // ---------------------------------------------------------------- math
+// packed fp32 pairs (FFMA2 / FADD2 on sm_100): two lanes of work per issue slot
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(reinterpret_cast<uint64_t&>(d))
+        : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)), "l"(reinterpret_cast<uint64_t&>(c)));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    float2 d;
+    asm("add.rn.f32x2 %0, %1, %2;"
+        : "=l"(reinterpret_cast<uint64_t&>(d))
+        : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+    return d;
+}
 __device__ __forceinline__ float ex2(float x) {  // MUFU.EX2, flushes denormals, ex2(-inf) = 0
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

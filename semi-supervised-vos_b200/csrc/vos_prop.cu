@@ -178,7 +178,7 @@ int vosprop_create(const vosprop_config* cfg, vosprop_engine** out) {
 
     const size_t rows = static_cast<size_t>(cfg->ring_slots) * e->p_pad_cap;
     const int tiles_cap = e->p_pad_cap / vosk::kTile;
-    e->partial_records = static_cast<size_t>(e->num_sms) * ((tiles_cap + e->num_sms - 1) / e->num_sms + 2) * 2;
+    e->partial_records = static_cast<size_t>(e->num_sms) * ((tiles_cap + e->num_sms - 1) / e->num_sms + 2) * vosk::kIdxSub;
     cudaError_t a1 = cudaMalloc(&e->ring_hi, rows * vosk::kK * 2);
     cudaError_t a2 = cudaMalloc(&e->ring_lo, rows * vosk::kK * 2);
     cudaError_t a3 = cudaMalloc(&e->meta, rows * vosk::kMetaFloats * 4);
@@ -343,7 +343,7 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     int kernel = s->kernel;
     if (kernel == VOSPROP_KERNEL_TC && (!all_index || e->W_d < 32)) kernel = VOSPROP_KERNEL_TC_DENSE;
     const vosd::Decomp dec = vosd::make_decomp(e->P, s->n_refs, e->num_sms);
-    if (static_cast<size_t>(dec.grid) * dec.max_segs * 2 > e->partial_records)
+    if (static_cast<size_t>(dec.grid) * dec.max_segs * vosk::kIdxSub > e->partial_records)
         return fail(VOSPROP_ERR_UNSUPPORTED, "partial buffer too small (grid %d x segs %d)", dec.grid, dec.max_segs);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     {
@@ -356,6 +356,7 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     mp.n_pixels = e->P; mp.p_pad = e->p_pad; mp.w_lowres = e->W_d; mp.h_lowres = e->H_d; mp.n_refs = s->n_refs;
     mp.num_sms = e->num_sms; mp.d = e->d; mp.H = e->H; mp.W = e->W; mp.q_slot = q_slot;
     mp.write_labels = s->write_labels; mp.probability = s->probability_propagation;
+    mp.n_sub = (kernel == VOSPROP_KERNEL_TC) ? vosk::kIdxSub : 2;
     mp.partials = e->partials; mp.meta = e->meta; mp.cls = e->cls;
     mp.out_prediction = s->out_prediction; mp.out_mask_lowres = s->out_mask_lowres; mp.out_mask_fullres = s->out_mask_fullres;
     {
