@@ -155,6 +155,22 @@ def main():
     np.savez_compressed(OUT / 'vosnet_forward.npz', y=y.numpy())
     meta['vosnet_forward'] = dict(keys={k: list(v.shape) for k, v in sd.items()}, input_seed=3,
                                   input_shape=[1, 3, 64, 96])
+    # ---- signatures of the drop-in callables
+    import inspect
+    sig = lambda f: list(inspect.signature(f).parameters)  # noqa: E731
+    sys.path.insert(0, str(ref.root))
+    try:
+        import importlib
+        inf = importlib.import_module('src.inference')
+    finally:
+        sys.path.remove(str(ref.root))
+    meta['signatures'] = {
+        'predict': sig(ref.predict.predict), 'sample_frames': sig(ref.predict.sample_frames),
+        'prepare_first_frame': sig(ref.predict.prepare_first_frame), 'get_labels': sig(ref.predict.get_labels),
+        'get_spatial_weight': sig(ref.predict.get_spatial_weight),
+        'inference_single': sig(ref.inference_utils.inference_single),
+        'inference_command_impl': sig(inf.inference_command_impl),
+        'inference_command_options': [p.name for p in inf.inference_command.params]}
     (OUT / 'meta.json').write_text(json.dumps(meta, indent=1, sort_keys=True))
     print('wrote', sorted(p.name for p in OUT.iterdir()))
 
