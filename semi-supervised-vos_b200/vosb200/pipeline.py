@@ -21,14 +21,19 @@ from .sequence import start_sequence
 class ClipSegmenter:
     def __init__(self, model: torch.nn.Module, device=None, sigma_1: float = 8.0, sigma_2: float = 21.0,
                  frame_range: int = 40, ref_num: int = 9, temperature: float = 1.0,
-                 probability_propagation: bool = False, backbone_batch: int = 10, amp: bool = True,
-                 channels_last: bool = True, kernel: int = capi.KERNEL_TC):
+                 probability_propagation: bool = False, backbone_batch: int = 35, amp: bool = True,
+                 channels_last: bool = True, kernel: int = capi.KERNEL_TC, fuse_backbone: bool = True):
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self.model = model.to(self.device).eval()
         if channels_last:
             self.model = self.model.to(memory_format=torch.channels_last)
         self.channels_last = channels_last
         self.amp = amp
+        # cuDNN-fused inference form (BN folded, bias/ReLU/residual in the conv epilogue) when available
+        self.fused = None
+        if fuse_backbone and amp and getattr(model, 'model', None) in ('resnet18', 'resnet50', 'resnet101'):
+            from .fused_backbone import FusedVOSNet
+            self.fused = FusedVOSNet(self.model)
         self.params = dict(sigma_1=sigma_1, sigma_2=sigma_2, frame_range=frame_range, ref_num=ref_num,
                            temperature=temperature, probability_propagation=probability_propagation)
         self.backbone_batch = backbone_batch
@@ -45,6 +50,8 @@ class ClipSegmenter:
 
     @torch.no_grad()
     def embed(self, frames: torch.Tensor) -> torch.Tensor:
+        if self.fused is not None:
+            return self.fused(frames)
         x = frames.contiguous(memory_format=torch.channels_last) if self.channels_last else frames
         with torch.autocast('cuda', dtype=torch.float16, enabled=self.amp):
             return self.model(x)

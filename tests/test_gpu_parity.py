@@ -155,3 +155,41 @@ def test_error_paths():
     with pytest.raises(VosPropError):
         eng.reset(120, 200, 960, 1600, 3)  # beyond capacity
     torch.cuda.synchronize()
+
+
+def test_fused_backbone_matches_module_graph():
+    """BN-folded cuDNN-fused trunk vs the stock VOSNet module graph (fp32) on the same weights."""
+    from oracle.fixtures import seeded_state_dict
+    from src.model.vos_net import VOSNet
+    from vosb200.fused_backbone import FusedVOSNet
+    net = VOSNet('resnet50', pretrained=False).eval()
+    net.load_state_dict(seeded_state_dict(net.state_dict()))
+    net = net.cuda()
+    x = torch.randn(2, 3, 96, 160, device='cuda', generator=torch.Generator(device='cuda').manual_seed(0))
+    with torch.no_grad():
+        want = net(x)
+        got = FusedVOSNet(net)(x).float()
+    rel = float((got - want).abs().max() / want.abs().max())
+    print(f'fused backbone: max rel err {rel:.3e}')
+    assert got.shape == want.shape and rel < 2e-2      # fp16 convolutions
+
+
+def test_clip_segmenter_end_to_end_matches_stepwise_engine():
+    """The public e2e call (pinned host frames -> masks on host) equals feeding its own embeddings through
+    the engine frame by frame."""
+    from oracle.fixtures import seeded_state_dict
+    from src.model.vos_net import VOSNet
+    from vosb200 import synthetic
+    from vosb200.pipeline import ClipSegmenter
+    from vosb200.sequence import propagate_clip
+    net = VOSNet('resnet50', pretrained=False).eval()
+    net.load_state_dict(seeded_state_dict(net.state_dict()))
+    seg = ClipSegmenter(net, backbone_batch=4)
+    frames, first = synthetic.clip_frames(9, 256, 320, 2, seed=3, device='cuda')
+    masks = seg.segment(frames, first)
+    assert masks.shape == (8, 256, 320) and masks.dtype == torch.uint8 and not masks.is_cuda
+    feats = torch.cat([seg.embed(frames[i:i + 4].cuda()) for i in range(0, 9, 4)]).float()
+    want = propagate_clip(_engine(feats.shape[2] * feats.shape[3]), feats, first.cuda())
+    agree = float((masks.cuda() == want).float().mean())
+    print(f'ClipSegmenter vs stepwise: {agree:.6f}')
+    assert agree >= MASK_AGREE
