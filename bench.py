@@ -42,6 +42,9 @@ import torch  # noqa: E402
 H, W, K = 480, 854, 256
 REF_NUM, FRAME_RANGE, SIGMA_1, SIGMA_2, TEMPERATURE = 9, 40, 8.0, 21.0, 1.0
 METRIC = 'propagated frames/sec at 480p'
+# dram__bytes_read.sum + dram__bytes_write.sum of one vos_affinity_idx launch (R = 9) from the ncu --set full
+# captures under profiles/ (see profiles/README.md); None until captured for that mode
+TRAFFIC_BYTES = {'f16': None, 'split3': 63.4e6}
 UNIT = 'frames/s'
 
 
@@ -53,6 +56,9 @@ def parse_args():
     ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
     ap.add_argument('--clips', type=int, default=4, help='clips per GPU per step')
     ap.add_argument('--frames', type=int, default=70, help='frames per clip')
+    ap.add_argument('--precision', choices=['f16', 'split3'], default='f16',
+                    help='embeddings resident in HBM for `value`: fp16 (what VOSNet emits under autocast; one exact '
+                         'tensor-core pass) or fp32 (bf16 hi+lo split, three passes)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ref-frames', type=int, default=2, help='reference arm: propagated frames per step')
@@ -64,8 +70,10 @@ def workload_config(args, n_gpus):
                         f'480x854 (60x107 stride-8 features, K=256), 2-4 objects',
             'clips_per_gpu': args.clips, 'frames_per_clip': args.frames, 'n_gpus': n_gpus,
             'ref_num': REF_NUM, 'frame_range': FRAME_RANGE, 'sigma': [SIGMA_1, SIGMA_2], 'temperature': TEMPERATURE,
-            'precision': 'bf16x3 split (hi*hi + lo*hi + hi*lo) tcgen05, fp32 accumulate/softmax',
-            'l2': 'inputs larger than L2 (1.8 GB of embeddings per step; 126 MB L2)',
+            'precision': ('fp16 embeddings (VOSNet under autocast, as the reference on CUDA): one tcgen05 kind::f16 pass, '
+                          'products exact in the fp32 accumulator, fp32 softmax' if args.precision == 'f16' else
+                          'fp32 embeddings: bf16x3 split (hi*hi + lo*hi + hi*lo) tcgen05, fp32 accumulate/softmax'),
+            'l2': f'inputs larger than L2 ({0.9 if args.precision == "f16" else 1.8:.1f} GB of embeddings per step; 126 MB L2)',
             'value_scope': 'propagation stage: append + fused affinity + merge/write-back; embeddings resident in HBM',
             'e2e_scope': 'ClipSegmenter.segment: pinned host frames -> H2D -> VOSNet(cuDNN, fp16 autocast) -> propagation -> uint8 masks -> D2H'}
 
@@ -217,6 +225,9 @@ def run_ours(args, rank, world, local_rank):
     C, T = args.clips, args.frames
     n_obj = [2 + (i + rank) % 3 for i in range(C)]
     clips = [synthetic.clip_features(T, H, W, n_obj[i], seed=1000 * rank + i, device=dev) for i in range(C)]
+    if args.precision == 'f16':
+        clips = [(f.half(), first) for f, first in clips]
+    passes = 1 if args.precision == 'f16' else 3
     P = clips[0][0].shape[2] * clips[0][0].shape[3]
     eng = PropagationEngine(max_pixels=P, ring_slots=48, device=dev)
     masks_keep = [None] * C
@@ -255,15 +266,16 @@ def run_ours(args, rank, world, local_rank):
     aff_ms, aff_n = stage['affinity']
     peak_tf, peak_hbm, peak_src = measured_peaks()
     achieved_tf = flops / (aff_ms * 1e-3) / 1e12 if aff_ms > 0 else 0.0
-    roofline = {'bound': 'tensor', 'kernel': 'vos_affinity_tc', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                'frac': achieved_tf / peak_tf, 'traffic': None, 'peak_source': peak_src,
-                'issued_tflops': 3 * achieved_tf, 'issued_frac': 3 * achieved_tf / peak_tf,
+    roofline = {'bound': 'tensor', 'kernel': 'vos_affinity_idx', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                'frac': achieved_tf / peak_tf, 'traffic': TRAFFIC_BYTES.get(args.precision), 'peak_source': peak_src,
+                'issued_tflops': passes * achieved_tf, 'issued_frac': passes * achieved_tf / peak_tf,
                 'launches': aff_n, 'avg_launch_us': aff_ms * 1e3 / max(aff_n, 1),
-                'note': 'achieved counts algorithmic FLOPs 2*P*N*K; the bf16x3 split issues 3x that on the tensor pipe'}
+                'note': 'achieved counts algorithmic FLOPs 2*P*N*K per launch; tensor-core passes issued per logit: '
+                        f'{passes}; traffic = dram bytes read+written per launch from the ncu capture in profiles/ (null: not captured)'}
     # HBM-bound side kernels: algorithmic bytes per launch
     app_ms, app_n = stage['append']
     mrg_ms, mrg_n = stage['merge']
-    app_bytes = P * K * 4 + 2 * P * K * 2
+    app_bytes = P * K * 2 * 2 if args.precision == 'f16' else P * K * 4 + 2 * P * K * 2
     mrg_bytes = 2 * 2 * 16 * 4 * P + 14 * 4 * P + H * W
     side = {'append': {'avg_launch_us': app_ms * 1e3 / max(app_n, 1), 'achieved_gbs': app_bytes * app_n / (app_ms * 1e-3) / 1e9 if app_ms else None,
                        'bytes_per_launch': app_bytes},
@@ -314,7 +326,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'bf16x3', 'data': 'synthetic', 'config': workload_config(args, world),
+                'dtype': 'f16' if args.precision == 'f16' else 'bf16x3', 'data': 'synthetic', 'config': workload_config(args, world),
                 'clocks': clocks.summary(), 'e2e': e2e, 'gpu_launches': int(gpu_launches),
                 'roofline': roofline, 'side_kernels': side, 'cpu_baseline': cpu}
         print(json.dumps(line), flush=True)

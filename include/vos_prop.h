@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define VOSPROP_ABI_VERSION 1
+#define VOSPROP_ABI_VERSION 2
 #define VOSPROP_MAX_REFS 32     /* reference frames per step (reference default ref_num = 9)   */
 #define VOSPROP_MAX_CLASSES 14  /* d = objects + 1 (DAVIS <= 11, YouTube-VOS <= 11)            */
 #define VOSPROP_FEAT_DIM 256    /* VOSNet embedding width, src/model/vos_net.py:22             */
@@ -34,6 +34,15 @@ enum vosprop_status {
 };
 
 enum vosprop_dtype { VOSPROP_F32 = 0, VOSPROP_F16 = 1, VOSPROP_BF16 = 2 };
+/* How the reference memory stores embeddings, fixed per video by vosprop_reset():
+ *   SPLIT3 : any input dtype; x = hi + lo (two bf16), S = Qhi.Rhi + Qlo.Rhi + Qhi.Rlo on the tensor cores
+ *            (3 passes, fp32 accumulate) -- fp32-grade logits from fp32 embeddings.
+ *   F16    : embeddings must arrive as fp16 -- what VOSNet emits under CUDA autocast, the reference's own
+ *            GPU path (src/utils/inference_utils.py:35,52-53).  The product of two fp16 values is exact in
+ *            the fp32 accumulator, so ONE tensor-core pass equals the fp32 contraction of those embeddings.
+ *   BF16   : same for bf16 embeddings.
+ * F16/BF16 refuse an append of any other dtype (it would round the embeddings). */
+enum vosprop_precision { VOSPROP_PREC_SPLIT3 = 0, VOSPROP_PREC_F16 = 1, VOSPROP_PREC_BF16 = 2 };
 /* memory order of a feature map handed to vosprop_append_features */
 enum vosprop_layout { VOSPROP_NCHW = 0 /* (K, H_d*W_d), torch default */, VOSPROP_NHWC = 1 /* (H_d*W_d, K) */ };
 enum vosprop_kernel {
@@ -82,8 +91,10 @@ void vosprop_destroy(vosprop_engine* e);
 /* New video: geometry + class count.  Replaces the state reset at a video boundary
  * (src/utils/inference_utils.py:28-48) and the prior set-up of prepare_first_frame
  * (src/model/predict.py:117-118: the (P,P) Gaussian matrices are never built; the kernel
- * evaluates the closed form).  H_d, W_d: feature-map size; H, W: full frame size; d: classes. */
-int vosprop_reset(vosprop_engine* e, int32_t H_d, int32_t W_d, int32_t H, int32_t W, int32_t d, void* stream);
+ * evaluates the closed form).  H_d, W_d: feature-map size; H, W: full frame size; d: classes;
+ * precision: storage / tensor-core mode of the reference memory for this video. */
+int vosprop_reset(vosprop_engine* e, int32_t H_d, int32_t W_d, int32_t H, int32_t W, int32_t d,
+                  int32_t precision /* enum vosprop_precision */, void* stream);
 
 /* Append frame `frame_idx`'s embedding to the ring (slot = frame_idx % ring_slots).  Replaces
  * `feats_history = torch.cat(...)` (inference_utils.py:72, :36).  `features`: device pointer to

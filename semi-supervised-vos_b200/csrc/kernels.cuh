@@ -60,7 +60,24 @@ struct AffinityParams {
     const __nv_bfloat16* ring_lo;
     const uint8_t* cls;   // [slots * p_pad] class id per reference pixel (0xFF = padding), index-label mode
     float inv_w;          // 1 / W_d
+    uint32_t idesc;       // tcgen05 instruction descriptor (f16 or bf16 operands, fp32 accumulate, 128x128)
+    int32_t feat_fmt;     // kFmtSplit: ring_hi/ring_lo = bf16 hi + lo; kFmtF16 / kFmtBF16: ring_hi only, one pass
 };
+
+enum : int32_t { kFmtSplit = 0, kFmtF16 = 1, kFmtBF16 = 2 };
+
+// feature (row, k) as fp32, whatever the ring's format (SIMT checker, top-k finish)
+__device__ __forceinline__ float2 ring_feat2(const AffinityParams& prm, size_t row, int k2) {
+    const size_t off = row * (kK / 2) + k2;
+    if (prm.feat_fmt == kFmtF16) return __half22float2(reinterpret_cast<const __half2*>(prm.ring_hi)[off]);
+    float2 h = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(prm.ring_hi)[off]);
+    if (prm.feat_fmt == kFmtSplit) {
+        const float2 l = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(prm.ring_lo)[off]);
+        h.x += l.x;
+        h.y += l.y;
+    }
+    return h;
+}
 
 // -------------------------------------------------------------------------------------------
 // Streaming softmax + prior + label gather for one target pixel (one thread).
@@ -179,6 +196,8 @@ vos_affinity_tc(const __grid_constant__ CUtensorMap tmap_hi, const __grid_consta
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const vosd::Decomp dec = vosd::make_decomp(prm.n_pixels, prm.n_refs, prm.num_sms);
+    const bool split = prm.feat_fmt == kFmtSplit;          // bf16 hi+lo (3 passes) or one exact 16-bit pass
+    const int n_chunks = split ? 2 * kNKC : kNKC;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_hi);
@@ -197,7 +216,7 @@ vos_affinity_tc(const __grid_constant__ CUtensorMap tmap_hi, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ================= TMA producer: target tile per segment, 8 reference chunks per tile.
+        // ================= TMA producer: target tile per segment, 8 (split) or 4 (single pass) reference chunks per tile.
         // Whole warp in the (uniform) control flow, elect.sync picks the issuing lane.
         vosd::SegIter it(dec, blockIdx.x);
         int m_tile, n0, n1;
@@ -206,22 +225,22 @@ vos_affinity_tc(const __grid_constant__ CUtensorMap tmap_hi, const __grid_consta
             if (it.seg > 0) mbar_wait(q_empty, (it.seg - 1) & 1);
             const int q_row = prm.q_slot * prm.p_pad + m_tile * kTile;
             if (elect_one()) {
-                mbar_arrive_expect_tx(q_full, kQBytes);
+                mbar_arrive_expect_tx(q_full, split ? kQBytes : kQBytes / 2);
                 for (int kc = 0; kc < kNKC; ++kc) {
                     tma_load_2d(q_smem + kc * kChunkBytes, &tmap_hi, kc * kKC, q_row, q_full);
-                    tma_load_2d(q_smem + (kNKC + kc) * kChunkBytes, &tmap_lo, kc * kKC, q_row, q_full);
+                    if (split) tma_load_2d(q_smem + (kNKC + kc) * kChunkBytes, &tmap_lo, kc * kKC, q_row, q_full);
                 }
             }
             __syncwarp();
             for (int nt = n0; nt < n1; ++nt) {
                 const int r = nt / dec.tpf;
                 const int row0 = prm.ref_slot[r] * prm.p_pad + (nt - r * dec.tpf) * kTile;
-                for (int c = 0; c < 2 * kNKC; ++c) {
+                for (int c = 0; c < n_chunks; ++c) {
                     mbar_wait_relaxed(&empty[stage], phase ^ 1, 64);
                     if (elect_one()) {
                         mbar_arrive_expect_tx(&full[stage], kChunkBytes);
-                        tma_load_2d(r_smem + stage * kChunkBytes, (c & 1) ? &tmap_lo : &tmap_hi, (c >> 1) * kKC,
-                                    row0, &full[stage]);
+                        tma_load_2d(r_smem + stage * kChunkBytes, (split && (c & 1)) ? &tmap_lo : &tmap_hi,
+                                    (split ? (c >> 1) : c) * kKC, row0, &full[stage]);
                     }
                     __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -230,7 +249,7 @@ vos_affinity_tc(const __grid_constant__ CUtensorMap tmap_hi, const __grid_consta
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one elected lane issues; SS form: A and B from shared memory)
-        constexpr uint32_t idesc = umma_idesc_bf16_f32(kTile, kTile);
+        const uint32_t idesc = prm.idesc;
         vosd::SegIter it(dec, blockIdx.x);
         int m_tile, n0, n1;
         uint32_t stage = 0, phase = 0, tile_count = 0;
@@ -245,9 +264,9 @@ vos_affinity_tc(const __grid_constant__ CUtensorMap tmap_hi, const __grid_consta
                 mbar_wait_relaxed(&acc_empty[buf], aphase ^ 1, 32);
                 tc_fence_after_sync();
                 const uint32_t d_tmem = tmem_base + buf * kTile;
-#pragma unroll
-                for (int c = 0; c < 2 * kNKC; ++c) {
-                    const int kc = c >> 1;
+                for (int c = 0; c < n_chunks; ++c) {
+                    const int kc = split ? (c >> 1) : c;
+                    const bool lo_chunk = split && (c & 1);
                     mbar_wait(&full[stage], phase);
                     tc_fence_after_sync();
                     if (elect_one()) {
@@ -255,17 +274,19 @@ vos_affinity_tc(const __grid_constant__ CUtensorMap tmap_hi, const __grid_consta
                         const uint64_t b_desc = r_desc0 + static_cast<uint64_t>(stage * (kChunkBytes >> 4));
                         const uint64_t a_hi = q_desc0 + static_cast<uint64_t>(kc * (kChunkBytes >> 4));
                         const uint64_t a_lo = q_desc0 + static_cast<uint64_t>((kNKC + kc) * (kChunkBytes >> 4));
-                        if ((c & 1) == 0) {   // reference hi chunk: Qhi.Rhi + Qlo.Rhi
+                        if (!lo_chunk) {      // reference hi chunk: Qhi.Rhi (+ Qlo.Rhi)
 #pragma unroll
                             for (int k = 0; k < kKC / 16; ++k) umma_bf16_ss(d_tmem, a_hi + 2 * k, b_desc + 2 * k, idesc, (c | k) != 0);
+                            if (split) {
 #pragma unroll
-                            for (int k = 0; k < kKC / 16; ++k) umma_bf16_ss(d_tmem, a_lo + 2 * k, b_desc + 2 * k, idesc, 1);
+                                for (int k = 0; k < kKC / 16; ++k) umma_bf16_ss(d_tmem, a_lo + 2 * k, b_desc + 2 * k, idesc, 1);
+                            }
                         } else {              // reference lo chunk: Qhi.Rlo
 #pragma unroll
                             for (int k = 0; k < kKC / 16; ++k) umma_bf16_ss(d_tmem, a_hi + 2 * k, b_desc + 2 * k, idesc, 1);
                         }
                         umma_commit(&empty[stage]);                       // smem stage free once these MMAs retire
-                        if (c == 2 * kNKC - 1) umma_commit(&acc_full[buf]);  // accumulator complete -> epilogue
+                        if (c == n_chunks - 1) umma_commit(&acc_full[buf]);  // accumulator complete -> epilogue
                     }
                     __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -375,10 +396,9 @@ __global__ void __launch_bounds__(kSimtThreads, 1) vos_affinity_simt(const Affin
         const size_t q_row = static_cast<size_t>(prm.q_slot) * prm.p_pad + m_tile * kTile;
         for (int i = tid; i < kTile * (kK / 2); i += kSimtThreads) {
             const int rr = i / (kK / 2), k2 = i % (kK / 2);
-            const float2 h = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(prm.ring_hi + (q_row + rr) * kK)[k2]);
-            const float2 l = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(prm.ring_lo + (q_row + rr) * kK)[k2]);
-            qs[rr * kQsStride + 2 * k2] = h.x + l.x;
-            qs[rr * kQsStride + 2 * k2 + 1] = h.y + l.y;
+            const float2 f = ring_feat2(prm, q_row + rr, k2);
+            qs[rr * kQsStride + 2 * k2] = f.x;
+            qs[rr * kQsStride + 2 * k2 + 1] = f.y;
         }
         RowAcc<D> st;
         st.init();
@@ -395,10 +415,9 @@ __global__ void __launch_bounds__(kSimtThreads, 1) vos_affinity_simt(const Affin
                 for (int i = tid; i < 64 * (kK / 2); i += kSimtThreads) {
                     const int cc = i / (kK / 2), k2 = i % (kK / 2);
                     const int col = (cc >> 5) * 64 + ch * 32 + (cc & 31);
-                    const float2 h = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(prm.ring_hi + (row0 + col) * kK)[k2]);
-                    const float2 l = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(prm.ring_lo + (row0 + col) * kK)[k2]);
-                    rs[cc * kK + 2 * k2] = h.x + l.x;
-                    rs[cc * kK + 2 * k2 + 1] = h.y + l.y;
+                    const float2 f = ring_feat2(prm, row0 + col, k2);
+                    rs[cc * kK + 2 * k2] = f.x;
+                    rs[cc * kK + 2 * k2 + 1] = f.y;
                 }
                 __syncthreads();
                 float v[32];
@@ -532,38 +551,87 @@ template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; 
 template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
 template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
-__device__ __forceinline__ void split_store(float x0, float x1, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t off) {
+// Stores one channel pair in the ring's format: bf16 hi + lo (kFmtSplit), or a single fp16 / bf16 value
+// (exact when the source already has that type -- the host refuses anything else in those modes).
+__device__ __forceinline__ uint32_t pack_hi(float x0, float x1, int fmt, uint32_t& lo_bits) {
+    if (fmt == kFmtF16) {
+        const __half2 h = __floats2half2_rn(x0, x1);
+        return reinterpret_cast<const uint32_t&>(h);
+    }
     const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-    *reinterpret_cast<__nv_bfloat162*>(hi + off) = __halves2bfloat162(h0, h1);
-    *reinterpret_cast<__nv_bfloat162*>(lo + off) = __halves2bfloat162(l0, l1);
+    const __nv_bfloat162 h = __halves2bfloat162(h0, h1);
+    if (fmt == kFmtSplit) {
+        const __nv_bfloat162 l = __halves2bfloat162(__float2bfloat16_rn(x0 - __bfloat162float(h0)),
+                                                    __float2bfloat16_rn(x1 - __bfloat162float(h1)));
+        lo_bits = reinterpret_cast<const uint32_t&>(l);
+    }
+    return reinterpret_cast<const uint32_t&>(h);
 }
 
+// Channel-major source (torch default): 32 pixels x 64 channels per block, transposed through shared memory.
 template <typename T>
 __global__ void __launch_bounds__(256) vos_append_nchw(const T* __restrict__ src, __nv_bfloat16* __restrict__ hi,
-                                                       __nv_bfloat16* __restrict__ lo, int n_pixels, size_t slot_row0) {
-    __shared__ float tile[kK][33];
-    const int p0 = blockIdx.x * 32;
+                                                       __nv_bfloat16* __restrict__ lo, int n_pixels, size_t slot_row0, int fmt) {
+    __shared__ float tile[64][33];
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int c = w; c < kK; c += 8) {
-        const int p = p0 + lane;
-        tile[c][lane] = p < n_pixels ? to_f32<T>(src[static_cast<size_t>(c) * n_pixels + p]) : 0.f;
+    const int p = p0 + lane;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = w * 8 + i;
+        tile[c][lane] = p < n_pixels ? to_f32<T>(src[static_cast<size_t>(c0 + c) * n_pixels + p]) : 0.f;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 32 * (kK / 2); i += 256) {
-        const int pix = i / (kK / 2), cp = i % (kK / 2);
-        if (p0 + pix < n_pixels)
-            split_store(tile[2 * cp][pix], tile[2 * cp + 1][pix], hi, lo, (slot_row0 + p0 + pix) * kK + 2 * cp);
+    uint32_t* hi32 = reinterpret_cast<uint32_t*>(hi);
+    uint32_t* lo32 = reinterpret_cast<uint32_t*>(lo);
+#pragma unroll
+    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+        const int pix = i >> 5, cp = i & 31;
+        if (p0 + pix < n_pixels) {
+            uint32_t lo_bits = 0;
+            const size_t off = ((slot_row0 + p0 + pix) * kK + c0) / 2 + cp;
+            hi32[off] = pack_hi(tile[2 * cp][pix], tile[2 * cp + 1][pix], fmt, lo_bits);
+            if (fmt == kFmtSplit) lo32[off] = lo_bits;
+        }
     }
+}
+
+// Pixel-major source (channels_last): elementwise convert, 8 channels per thread (16-byte stores).
+// Requires a 16-byte aligned source (the host falls back to the pair kernel otherwise).
+template <typename T>
+__global__ void __launch_bounds__(256) vos_append_nhwc8(const T* __restrict__ src, __nv_bfloat16* __restrict__ hi,
+                                                        __nv_bfloat16* __restrict__ lo, int n_pixels, size_t slot_row0, int fmt) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;  // group of 8 channels
+    if (i >= static_cast<size_t>(n_pixels) * (kK / 8)) return;
+    float x[8];
+    if (sizeof(T) == 4) {
+        const float4 a = reinterpret_cast<const float4*>(src)[2 * i], b = reinterpret_cast<const float4*>(src)[2 * i + 1];
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+        const uint4 raw = reinterpret_cast<const uint4*>(src)[i];
+        const T* e = reinterpret_cast<const T*>(&raw);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = to_f32<T>(e[k]);
+    }
+    uint4 h, l = make_uint4(0, 0, 0, 0);
+    h.x = pack_hi(x[0], x[1], fmt, l.x);
+    h.y = pack_hi(x[2], x[3], fmt, l.y);
+    h.z = pack_hi(x[4], x[5], fmt, l.z);
+    h.w = pack_hi(x[6], x[7], fmt, l.w);
+    const size_t off = slot_row0 * (kK / 8) + i;
+    reinterpret_cast<uint4*>(hi)[off] = h;
+    if (fmt == kFmtSplit) reinterpret_cast<uint4*>(lo)[off] = l;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) vos_append_nhwc(const T* __restrict__ src, __nv_bfloat16* __restrict__ hi,
-                                                       __nv_bfloat16* __restrict__ lo, int n_pixels, size_t slot_row0) {
+                                                       __nv_bfloat16* __restrict__ lo, int n_pixels, size_t slot_row0, int fmt) {
     const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;  // channel pair index
     if (i >= static_cast<size_t>(n_pixels) * (kK / 2)) return;
-    split_store(to_f32<T>(src[2 * i]), to_f32<T>(src[2 * i + 1]), hi, lo, slot_row0 * kK + 2 * i);
+    uint32_t lo_bits = 0;
+    const size_t off = slot_row0 * (kK / 2) + i;
+    reinterpret_cast<uint32_t*>(hi)[off] = pack_hi(to_f32<T>(src[2 * i]), to_f32<T>(src[2 * i + 1]), fmt, lo_bits);
+    if (fmt == kFmtSplit) reinterpret_cast<uint32_t*>(lo)[off] = lo_bits;
 }
 
 // -------------------------------------------------------------------------------------------

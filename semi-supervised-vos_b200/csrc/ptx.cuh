@@ -151,12 +151,13 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t smem_addr) {
     return static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) |
            (1ull << 46) | (2ull << 61);
 }
-// Instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, dense.
-//   [4,6) c_format=1(f32) | [7,10) a_format=1(bf16) | [10,13) b_format=1(bf16)
+// Instruction descriptor, kind::f16: D=f32, A and B of the same 16-bit format, both K-major, dense.
+//   [4,6) c_format=1(f32) | [7,10) a_format (0 = f16, 1 = bf16) | [10,13) b_format
 //   [15] a_major=0(K) | [16] b_major=0(K) | [17,23) N>>3 | [24,29) M>>4
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(uint32_t M, uint32_t N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc_f32acc(uint32_t M, uint32_t N, uint32_t ab_format) {
+    return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(uint32_t M, uint32_t N) { return umma_idesc_f32acc(M, N, 1u); }
 // D[tmem] (+)= A[smem] * B[smem]^T   (one thread issues for the CTA)
 __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
                                              uint32_t idesc, uint32_t accumulate) {
@@ -198,6 +199,18 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
     asm("add.rn.f32x2 %0, %1, %2;"
         : "=l"(reinterpret_cast<uint64_t&>(d))
         : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+    return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    float2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;"
+        : "=l"(reinterpret_cast<uint64_t&>(d))
+        : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+    return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {  // FMNMX3
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
     return d;
 }
 __device__ __forceinline__ float ex2(float x) {  // MUFU.EX2, flushes denormals, ex2(-inf) = 0

@@ -17,6 +17,9 @@
 #include "kernels.cuh"
 #include "affinity_idx.cuh"
 
+static_assert(VOSPROP_PREC_SPLIT3 == vosk::kFmtSplit && VOSPROP_PREC_F16 == vosk::kFmtF16 && VOSPROP_PREC_BF16 == vosk::kFmtBF16,
+              "precision enum and ring formats must coincide");
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -48,6 +51,7 @@ struct vosprop_engine {
     int p_pad_cap = 0;      // ring rows per slot at capacity
     // geometry of the current video
     int H_d = 0, W_d = 0, H = 0, W = 0, d = 0, P = 0, p_pad = 0;
+    int precision = VOSPROP_PREC_SPLIT3;
     __nv_bfloat16* ring_hi = nullptr;
     __nv_bfloat16* ring_lo = nullptr;
     float* meta = nullptr;
@@ -103,9 +107,12 @@ int encode_maps(vosprop_engine* e) {
 
 template <int D>
 int launch_affinity(vosprop_engine* e, const vosk::AffinityParams& prm, int grid, int kernel, cudaStream_t st) {
-    if (kernel == VOSPROP_KERNEL_TC) {
-        VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_idx<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kIdxSmem));
-        vosk::vos_affinity_idx<D><<<grid, vosk::kIdxThreads, vosk::kIdxSmem, st>>>(e->tmap_hi, e->tmap_lo, prm);
+    if (kernel == VOSPROP_KERNEL_TC && prm.feat_fmt == vosk::kFmtSplit) {
+        VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_idx<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kIdxSmem));
+        vosk::vos_affinity_idx<D, true><<<grid, vosk::kIdxThreads, vosk::kIdxSmem, st>>>(e->tmap_hi, e->tmap_lo, prm);
+    } else if (kernel == VOSPROP_KERNEL_TC) {
+        VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_idx<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kIdxSmem));
+        vosk::vos_affinity_idx<D, false><<<grid, vosk::kIdxThreads, vosk::kIdxSmem, st>>>(e->tmap_hi, e->tmap_lo, prm);
     } else if (kernel == VOSPROP_KERNEL_TC_DENSE) {
         VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kSmemTc));
         vosk::vos_affinity_tc<D><<<grid, vosk::kTcThreads, vosk::kSmemTc, st>>>(e->tmap_hi, e->tmap_lo, prm);
@@ -212,8 +219,10 @@ void vosprop_destroy(vosprop_engine* e) {
     delete e;
 }
 
-int vosprop_reset(vosprop_engine* e, int32_t H_d, int32_t W_d, int32_t H, int32_t W, int32_t d, void* stream) {
+int vosprop_reset(vosprop_engine* e, int32_t H_d, int32_t W_d, int32_t H, int32_t W, int32_t d, int32_t precision,
+                  void* stream) {
     if (!e) return fail(VOSPROP_ERR_INVALID, "null engine");
+    if (precision < VOSPROP_PREC_SPLIT3 || precision > VOSPROP_PREC_BF16) return fail(VOSPROP_ERR_INVALID, "unknown precision %d", precision);
     if (H_d <= 0 || W_d <= 0 || H <= 0 || W <= 0) return fail(VOSPROP_ERR_INVALID, "bad geometry %dx%d / %dx%d", H_d, W_d, H, W);
     if (d < 1 || d > VOSPROP_MAX_CLASSES) return fail(VOSPROP_ERR_UNSUPPORTED, "d=%d classes; supported 1..%d", d, VOSPROP_MAX_CLASSES);
     const int64_t P = static_cast<int64_t>(H_d) * W_d;
@@ -221,6 +230,7 @@ int vosprop_reset(vosprop_engine* e, int32_t H_d, int32_t W_d, int32_t H, int32_
     if (W_d > 4096) return fail(VOSPROP_ERR_UNSUPPORTED, "W_d=%d too wide", W_d);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     e->H_d = H_d; e->W_d = W_d; e->H = H; e->W = W; e->d = d;
+    e->precision = precision;
     e->P = static_cast<int>(P);
     e->p_pad = (e->P + vosk::kTile - 1) / vosk::kTile * vosk::kTile;
     int rc = encode_maps(e);
@@ -244,19 +254,29 @@ int vosprop_append_features(vosprop_engine* e, int32_t frame_idx, const void* fe
     const int slot = frame_idx % e->cfg.ring_slots;
     const size_t row0 = static_cast<size_t>(slot) * e->p_pad;
     const int P = e->P;
+    if (dtype != VOSPROP_F32 && dtype != VOSPROP_F16 && dtype != VOSPROP_BF16) return fail(VOSPROP_ERR_INVALID, "unknown dtype %d", dtype);
+    if ((e->precision == VOSPROP_PREC_F16 && dtype != VOSPROP_F16) || (e->precision == VOSPROP_PREC_BF16 && dtype != VOSPROP_BF16))
+        return fail(VOSPROP_ERR_INVALID, "this video was reset in %s precision: embeddings must arrive in that dtype (got dtype %d); "
+                    "use VOSPROP_PREC_SPLIT3 for fp32 embeddings", e->precision == VOSPROP_PREC_F16 ? "F16" : "BF16", dtype);
+    const int fmt = e->precision;   // enum values coincide with vosk::kFmt*
     TimedLaunch timed(e, VOSPROP_T_APPEND, st);
     if (layout == VOSPROP_NCHW) {
-        const unsigned grid = (P + 31) / 32;
-        if (dtype == VOSPROP_F32) vosk::vos_append_nchw<float><<<grid, 256, 0, st>>>(static_cast<const float*>(features), e->ring_hi, e->ring_lo, P, row0);
-        else if (dtype == VOSPROP_F16) vosk::vos_append_nchw<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(features), e->ring_hi, e->ring_lo, P, row0);
-        else if (dtype == VOSPROP_BF16) vosk::vos_append_nchw<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(features), e->ring_hi, e->ring_lo, P, row0);
-        else return fail(VOSPROP_ERR_INVALID, "unknown dtype %d", dtype);
+        const dim3 grid((P + 31) / 32, vosk::kK / 64);
+        if (dtype == VOSPROP_F32) vosk::vos_append_nchw<float><<<grid, 256, 0, st>>>(static_cast<const float*>(features), e->ring_hi, e->ring_lo, P, row0, fmt);
+        else if (dtype == VOSPROP_F16) vosk::vos_append_nchw<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(features), e->ring_hi, e->ring_lo, P, row0, fmt);
+        else vosk::vos_append_nchw<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(features), e->ring_hi, e->ring_lo, P, row0, fmt);
     } else if (layout == VOSPROP_NHWC) {
-        const unsigned grid = static_cast<unsigned>((static_cast<size_t>(P) * (vosk::kK / 2) + 255) / 256);
-        if (dtype == VOSPROP_F32) vosk::vos_append_nhwc<float><<<grid, 256, 0, st>>>(static_cast<const float*>(features), e->ring_hi, e->ring_lo, P, row0);
-        else if (dtype == VOSPROP_F16) vosk::vos_append_nhwc<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(features), e->ring_hi, e->ring_lo, P, row0);
-        else if (dtype == VOSPROP_BF16) vosk::vos_append_nhwc<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(features), e->ring_hi, e->ring_lo, P, row0);
-        else return fail(VOSPROP_ERR_INVALID, "unknown dtype %d", dtype);
+        if (reinterpret_cast<uintptr_t>(features) % 16 == 0) {
+            const unsigned grid = static_cast<unsigned>((static_cast<size_t>(P) * (vosk::kK / 8) + 255) / 256);
+            if (dtype == VOSPROP_F32) vosk::vos_append_nhwc8<float><<<grid, 256, 0, st>>>(static_cast<const float*>(features), e->ring_hi, e->ring_lo, P, row0, fmt);
+            else if (dtype == VOSPROP_F16) vosk::vos_append_nhwc8<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(features), e->ring_hi, e->ring_lo, P, row0, fmt);
+            else vosk::vos_append_nhwc8<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(features), e->ring_hi, e->ring_lo, P, row0, fmt);
+        } else {
+            const unsigned grid = static_cast<unsigned>((static_cast<size_t>(P) * (vosk::kK / 2) + 255) / 256);
+            if (dtype == VOSPROP_F32) vosk::vos_append_nhwc<float><<<grid, 256, 0, st>>>(static_cast<const float*>(features), e->ring_hi, e->ring_lo, P, row0, fmt);
+            else if (dtype == VOSPROP_F16) vosk::vos_append_nhwc<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(features), e->ring_hi, e->ring_lo, P, row0, fmt);
+            else vosk::vos_append_nhwc<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(features), e->ring_hi, e->ring_lo, P, row0, fmt);
+        }
     } else {
         return fail(VOSPROP_ERR_INVALID, "unknown layout %d", layout);
     }
@@ -338,6 +358,8 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     ap.scale2 = static_cast<float>(static_cast<double>(s->temperature) * 1.4426950408889634);
     ap.meta = e->meta; ap.partials = e->partials; ap.ring_hi = e->ring_hi; ap.ring_lo = e->ring_lo;
     ap.cls = e->cls; ap.inv_w = 1.0f / static_cast<float>(e->W_d);
+    ap.feat_fmt = e->precision;
+    ap.idesc = vosptx::umma_idesc_f32acc(vosk::kTile, vosk::kTile, e->precision == VOSPROP_PREC_F16 ? 0u : 1u);
     // the index-label kernel needs one class byte per reference pixel and W_d >= 32; anything else
     // (dense / probability labels, tiny maps) runs on the general tensor-core kernel
     int kernel = s->kernel;

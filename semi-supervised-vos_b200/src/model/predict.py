@@ -17,7 +17,7 @@ import torch
 from PIL import Image
 
 from src.config import Config
-from vosb200 import PropagationEngine, plan_refs
+from vosb200 import PropagationEngine, plan_refs, precision_for
 from vosb200 import sample_frames as _sample_frames
 from vosb200.sequence import first_frame_lowres
 
@@ -72,7 +72,9 @@ def predict(ref, target, ref_label, weight_dense, weight_sparse, frame_idx, rang
     eng = _SCRATCH.get(key)
     if eng is None:
         eng = _SCRATCH[key] = PropagationEngine(max_pixels=P, ring_slots=33, device=dev)
-    eng.reset(H_d, W_d, H_d * 8, W_d * 8, d)
+    if ref.dtype != target.dtype:
+        ref = ref.to(target.dtype)
+    eng.reset(H_d, W_d, H_d * 8, W_d * 8, d, precision_for(target.dtype))
     for slot, f in enumerate(frames):
         eng.append(slot, ref[f])
         eng.set_labels_dense(slot, ref_label[:, f])

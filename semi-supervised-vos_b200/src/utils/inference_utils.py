@@ -17,7 +17,7 @@ from src.config import Config
 from src.model.predict import prepare_first_frame
 from src.utils.utils import save_predictions
 from vosb200 import PropagationEngine
-from vosb200.engine import required_ring_slots
+from vosb200.engine import precision_for, required_ring_slots
 
 REDUCTIONS = {'maximum': lambda x, y: torch.maximum(x, y),
               'minimum': lambda x, y: torch.minimum(x, y),
@@ -87,7 +87,7 @@ def inference_single(model, inference_loader, total_len, annotation_dir, last_vi
             (_, _, H, W) = input.shape
             (_, _, H_d, W_d) = features.shape
             engine = _engine_for(H_d * W_d, slots)
-            engine.reset(H_d, W_d, H, W, int(d))
+            engine.reset(H_d, W_d, H, W, int(d), precision_for(features.dtype))   # fp16 under autocast -> one exact pass
             engine.append(0, features)
             engine.set_labels_index(0, label_1hot[:, 0].argmax(0))
             sink = _VideoSink(current_video, palette, save, H, W, features.device)

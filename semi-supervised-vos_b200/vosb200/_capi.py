@@ -10,6 +10,8 @@ FEAT_DIM = 256
 F32, F16, BF16 = 0, 1, 2
 NCHW, NHWC = 0, 1
 KERNEL_TC, KERNEL_SIMT, KERNEL_TC_DENSE = 0, 1, 2
+PREC_SPLIT3, PREC_F16, PREC_BF16 = 0, 1, 2
+ABI_VERSION = 2
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4
 
 LIB_PATH = Path(__file__).resolve().parent.parent / 'csrc' / 'libvosprop.so'
@@ -40,7 +42,7 @@ EXPORTS = {
     'vosprop_abi_version': (C.c_int, []),
     'vosprop_create': (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     'vosprop_destroy': (None, [C.c_void_p]),
-    'vosprop_reset': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    'vosprop_reset': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     'vosprop_append_features': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     'vosprop_set_labels_index': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'vosprop_set_labels_dense': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
@@ -69,7 +71,7 @@ def lib() -> C.CDLL:
         for name, (res, args) in EXPORTS.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.vosprop_abi_version() != 1:
+        if handle.vosprop_abi_version() != ABI_VERSION:
             raise ImportError('libvosprop ABI version mismatch; rebuild')
         _lib = handle
     return _lib

@@ -42,6 +42,12 @@ def plan_refs(frame_idx: int, take_range: int, num_refs: int, sigma_dense: float
     return list(st.ref_frames[:st.n_refs]), list(st.ref_sigma[:st.n_refs])
 
 
+def precision_for(dtype: torch.dtype) -> int:
+    """Storage mode that keeps embeddings of `dtype` exact: 16-bit floats go through the tensor cores in one
+    pass (their products are exact in the fp32 accumulator); fp32 needs the bf16 hi+lo split."""
+    return {torch.float16: capi.PREC_F16, torch.bfloat16: capi.PREC_BF16}.get(dtype, capi.PREC_SPLIT3)
+
+
 def required_ring_slots(frame_range: int, ref_num: int) -> int:
     """Slots needed so that every frame sample_frames can pick is still resident, plus the target."""
     return max(frame_range + CONTINUOUS_FRAME, ref_num) + 1
@@ -96,9 +102,12 @@ class PropagationEngine:
         return {k: (tot[i], cnt[i]) for i, k in enumerate(('append', 'affinity', 'merge'))}
 
     # ------------------------------------------------------------------ per-video state
-    def reset(self, H_d: int, W_d: int, H: int, W: int, d: int):
-        capi.check(self._lib.vosprop_reset(self._h, H_d, W_d, H, W, d, self._stream()))
+    def reset(self, H_d: int, W_d: int, H: int, W: int, d: int, precision: int = capi.PREC_SPLIT3):
+        """New video.  `precision`: PREC_SPLIT3 (any embedding dtype, bf16 hi+lo, 3 tensor-core passes) or
+        PREC_F16 / PREC_BF16 (embeddings already 16-bit: one exact pass); see precision_for()."""
+        capi.check(self._lib.vosprop_reset(self._h, H_d, W_d, H, W, d, int(precision), self._stream()))
         self.geom = (H_d, W_d, H, W, d)
+        self.precision = int(precision)
 
     def append(self, frame_idx: int, features: torch.Tensor):
         """features: (K,H_d,W_d) or (1,K,H_d,W_d), fp32/fp16/bf16, standard or channels_last."""

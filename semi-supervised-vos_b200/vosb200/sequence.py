@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from . import _capi as capi
-from .engine import PropagationEngine
+from .engine import PropagationEngine, precision_for
 
 SCALE = 0.125  # src/config.py:12
 
@@ -36,13 +36,14 @@ def first_frame_lowres(label_full: torch.Tensor, H_d: int, W_d: int) -> torch.Te
 
 
 def start_sequence(engine: PropagationEngine, first_features: torch.Tensor, first_label_full: torch.Tensor,
-                   d: Optional[int] = None) -> int:
-    """Frame 0: reset the engine, append its features, install the one-hot ground truth."""
+                   d: Optional[int] = None, precision: Optional[int] = None) -> int:
+    """Frame 0: reset the engine, append its features, install the one-hot ground truth.
+    The reference memory's precision follows the embeddings' dtype unless given (engine.precision_for)."""
     H, W = first_label_full.shape
     K, H_d, W_d = first_features.shape[-3:]
     if d is None:
         d = int(first_label_full.max().item()) + 1  # predict.py:113
-    engine.reset(H_d, W_d, H, W, d)
+    engine.reset(H_d, W_d, H, W, d, precision_for(first_features.dtype) if precision is None else precision)
     engine.append(0, first_features)
     engine.set_labels_index(0, first_frame_lowres(first_label_full.to(engine.device), H_d, W_d))
     return d
@@ -51,13 +52,13 @@ def start_sequence(engine: PropagationEngine, first_features: torch.Tensor, firs
 def propagate_clip(engine: PropagationEngine, features: torch.Tensor, first_label_full, sigma_1: float = 8.0,
                    sigma_2: float = 21.0, frame_range: int = 40, ref_num: int = 9, temperature: float = 1.0,
                    probability_propagation: bool = False, kernel: int = capi.KERNEL_TC, d: Optional[int] = None,
-                   return_predictions: bool = False):
+                   return_predictions: bool = False, precision: Optional[int] = None):
     """features (T,K,H_d,W_d) on the engine's device -> masks (T-1,H,W) uint8 on device
     (+ predictions (T-1,d,P) fp32 when asked).  No host sync inside."""
     first = torch.as_tensor(np.asarray(first_label_full)) if not torch.is_tensor(first_label_full) else first_label_full
     H, W = first.shape
     T = features.shape[0]
-    d = start_sequence(engine, features[0], first, d)
+    d = start_sequence(engine, features[0], first, d, precision)
     P = features.shape[2] * features.shape[3]
     masks = torch.empty((max(T - 1, 0), H, W), dtype=torch.uint8, device=engine.device)
     preds = torch.empty((T - 1, d, P), dtype=torch.float32, device=engine.device) if return_predictions else None

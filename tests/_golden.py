@@ -12,6 +12,9 @@ GOLDEN = Path(__file__).resolve().parent / 'golden'
 META = json.loads((GOLDEN / 'meta.json').read_text())
 GEN_KEYS = ('T', 'H', 'W', 'n_objects', 'seed', 'feat_scale')
 SEQ_NAMES = [k for k in META if k[0] in 'ABCDEFG' and k[1] == '_']
+META16 = json.loads((GOLDEN / 'meta16.json').read_text())   # oracle/make_golden_f16.py
+SEQ16_NAMES = sorted(META16)
+DTYPES = {'float16': torch.float16, 'bfloat16': torch.bfloat16}
 
 
 def sha(t):
@@ -27,6 +30,20 @@ def sequence_inputs(name):
     run = {k: v for k, v in cfg.items() if k in ('ref_num', 'frame_range', 'sigma_1', 'sigma_2',
                                                  'temperature', 'probability_propagation')}
     return feats, first, run
+
+
+def sequence16_inputs(tag):
+    """(16-bit embeddings, first annotation, run parameters): the seeded clip rounded once to fp16 / bf16."""
+    cfg = META16[tag]
+    feats, first, run = sequence_inputs(cfg['source'])
+    feats = feats.to(DTYPES[cfg['dtype']])
+    assert sha(feats.float()) == cfg['features_sha256']
+    return feats, first, run
+
+
+def sequence16_golden(tag):
+    z = np.load(GOLDEN / f'seq16_{tag}.npz')
+    return z['masks'], z['predictions']
 
 
 def sequence_golden(name):

@@ -50,6 +50,27 @@ def test_golden_sequences(name, kernel):
         assert err <= PROB_ATOL
 
 
+@pytest.mark.parametrize('kernel', KERNELS)
+@pytest.mark.parametrize('tag', G.SEQ16_NAMES)
+def test_golden_sequences_16bit_single_pass(tag, kernel):
+    """fp16 / bf16 embeddings (what VOSNet emits under autocast): ONE tensor-core pass, exact products.
+    Goldens: the reference's inference_single run in fp32 on the same 16-bit-valued embeddings."""
+    from vosb200 import PREC_BF16, PREC_F16
+    from vosb200.sequence import propagate_clip
+    feats, first, run = G.sequence16_inputs(tag)
+    masks_ref, preds_ref = G.sequence16_golden(tag)
+    eng = _engine(feats.shape[2] * feats.shape[3])
+    masks, preds = propagate_clip(eng, feats.cuda(), first, kernel=_kernels()[kernel], return_predictions=True, **run)
+    assert eng.precision == (PREC_F16 if feats.dtype == torch.float16 else PREC_BF16)
+    masks, preds = masks.cpu().numpy(), preds.cpu().numpy()
+    agree = float((masks == masks_ref).mean())
+    err = float(np.abs(preds - preds_ref).max())
+    print(f'{tag}/{kernel}: mask agreement {agree:.6f}, max |dP| {err:.3e}')
+    assert agree >= MASK_AGREE
+    if agree == 1.0 or run['probability_propagation']:
+        assert err <= PROB_ATOL
+
+
 @pytest.mark.parametrize('kernel', ['simt', 'tc_dense'])
 def test_golden_predict_cases_teacher_forced(kernel):
     """Stand-alone predict() calls with externally supplied label histories (teacher forcing:
@@ -83,14 +104,18 @@ def test_golden_predict_cases_teacher_forced(kernel):
         assert np.array_equal(out['mask_lowres'].cpu().numpy(), got.argmax(0).astype(np.uint8))
 
 
+@pytest.mark.parametrize('prec', ['split3', 'f16'])
 @pytest.mark.parametrize('kernel', KERNELS)
-def test_480p_against_oracle(kernel):
+def test_480p_against_oracle(kernel, prec):
     """480p (60x107 = 6420 pixels, 51 tiles, ragged last tile) vs the CPU oracle, teacher forced.
     Labels are class ids ('tc' -> index-label kernel) with a random history: every 32-pixel chunk is
     class-mixed, the hardest case for the ballot path."""
     from vosb200 import plan_refs
     T = 18
+    from vosb200 import PREC_F16, PREC_SPLIT3
     feats, first = O.synthetic_sequence(T, 480, 854, 2, seed=31, feat_scale=0.30)
+    if prec == 'f16':
+        feats = feats.half().float()     # the oracle sees exactly the values the engine stores
     _, K, H_d, W_d = feats.shape
     P = H_d * W_d
     low, d = O.first_frame_labels(first)
@@ -100,8 +125,8 @@ def test_480p_against_oracle(kernel):
     cls[0] = low
     hist = torch.stack([O.index_to_onehot(cls[f], d) for f in range(T)], 1)
     eng = _engine(P)
-    eng.reset(H_d, W_d, 480, 854, d)
-    gf = feats.cuda()
+    eng.reset(H_d, W_d, 480, 854, d, PREC_F16 if prec == 'f16' else PREC_SPLIT3)
+    gf = feats.cuda().half() if prec == 'f16' else feats.cuda()
     for f in range(T):
         eng.append(f, gf[f])
         eng.set_labels_index(f, cls[f].to(torch.uint8).cuda())
@@ -112,7 +137,7 @@ def test_480p_against_oracle(kernel):
         got = out['prediction'].cpu()
         err = float((got - want).abs().max())
         agree = float((got.argmax(0) == want.argmax(0)).float().mean())
-        print(f'480p t={t}/{kernel}: max |dP| {err:.3e}, argmax agreement {agree:.6f}')
+        print(f'480p t={t}/{kernel}/{prec}: max |dP| {err:.3e}, argmax agreement {agree:.6f}')
         assert err <= PROB_ATOL
         assert agree >= MASK_AGREE
         full = O.upsample_mask(out['mask_lowres'].cpu().long(), H_d, W_d, 480, 854)
@@ -150,6 +175,11 @@ def test_error_paths():
         eng.propagate(1, [5], [8.0])
     with pytest.raises(VosPropError):   # negative temperature unsupported (documented)
         eng.propagate(1, [0], [8.0], temperature=-1.0)
+    from vosb200 import PREC_F16
+    eng.reset(12, 20, 96, 160, 3, PREC_F16)
+    with pytest.raises(VosPropError):   # fp32 embeddings into an fp16 memory would be rounded: refused
+        eng.append(0, torch.zeros(256, 12, 20, device='cuda'))
+    eng.append(0, torch.zeros(256, 12, 20, device='cuda', dtype=torch.float16))
     with pytest.raises(VosPropError):
         eng.reset(12, 20, 96, 160, 15)  # too many classes
     with pytest.raises(VosPropError):

@@ -75,6 +75,17 @@ def test_sequences_match_reference_inference_single(name):
     assert np.array_equal(torch.stack(preds).numpy(), preds_ref)
 
 
+@pytest.mark.parametrize('tag', G.SEQ16_NAMES)
+def test_sequences_on_16bit_embeddings_match_reference(tag):
+    """Same pin for the inputs of the single-pass tensor-core modes: embeddings rounded once to fp16 / bf16
+    (what the reference's CUDA path sees after autocast), reference run in fp32 on them."""
+    feats, first, run = G.sequence16_inputs(tag)
+    masks_ref, preds_ref = G.sequence16_golden(tag)
+    masks, preds = O.propagate_sequence(feats.float(), first, **run)
+    assert np.array_equal(masks.numpy().astype(np.uint8), masks_ref)
+    assert np.array_equal(torch.stack(preds).numpy(), preds_ref)
+
+
 def test_topk_extension_reduces_to_reference_when_k_covers_everything():
     feats, hist, _ = G.predict_case_inputs()
     t = 10
