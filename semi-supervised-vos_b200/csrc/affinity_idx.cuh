@@ -43,9 +43,11 @@ struct IdxCfg {
     static constexpr int kQChunks = kSplit ? 8 : 4;            // 32-column TMEM chunks of the target tile
 };
 
-struct IdxPipe {
-    uint8_t* r_smem;
-    uint64_t *full, *empty, *q_full, *q_empty, *acc_full, *acc_empty;
+struct IdxPipe {              // 32-bit shared-window addresses, computed once per thread
+    uint32_t r_smem;          // kIdxStages x 16 KiB reference chunks
+    uint32_t full, empty;     // [kIdxStages] TMA -> MMA, MMA -> TMA
+    uint32_t q_full, q_empty; // epilogue threads -> MMA (target tile is in TMEM), MMA -> epilogue
+    uint32_t acc_full, acc_empty;  // [kIdxMaxAccBufs] MMA -> epilogue, epilogue -> MMA
     uint32_t tmem_base;
 };
 
@@ -68,14 +70,14 @@ __device__ __forceinline__ void idx_role_producer(const IdxPipe& pp, const CUten
             const int r = nt / dec.tpf;
             const int row0 = prm.ref_slot[r] * prm.p_pad + (nt - r * dec.tpf) * kTile;
             for (int c = 0; c < kChunks; ++c) {
-                mbar_wait_relaxed(&pp.empty[stage], phase ^ 1, 64);
+                mbar_wait_relaxed_s(pp.empty + 8 * stage, phase ^ 1, 64);
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(&pp.full[stage], kChunkBytes);
+                    mbar_arrive_expect_tx_s(pp.full + 8 * stage, kChunkBytes);
                     if (kSplit)
-                        tma_load_2d(pp.r_smem + stage * kChunkBytes, (c & 1) ? tmap_lo : tmap_hi, (c >> 1) * kKC, row0,
-                                    &pp.full[stage]);
+                        tma_load_2d_s(pp.r_smem + stage * kChunkBytes, (c & 1) ? tmap_lo : tmap_hi, (c >> 1) * kKC, row0,
+                                      pp.full + 8 * stage);
                     else
-                        tma_load_2d(pp.r_smem + stage * kChunkBytes, tmap_hi, c * kKC, row0, &pp.full[stage]);
+                        tma_load_2d_s(pp.r_smem + stage * kChunkBytes, tmap_hi, c * kKC, row0, pp.full + 8 * stage);
                 }
                 __syncwarp();
                 if (++stage == kIdxStages) { stage = 0; phase ^= 1; }
@@ -93,17 +95,17 @@ __device__ __forceinline__ void idx_role_mma(const IdxPipe& pp, const AffinityPa
     int m_tile, n0, n1;
     uint32_t stage = 0, phase = 0, buf = 0, aphase = 0;
     const uint32_t q_hi = pp.tmem_base + Cfg::kTmemQ, q_lo = pp.tmem_base + Cfg::kTmemQ + 128;
-    const uint64_t desc0 = umma_desc_kmajor_sw128(smem_u32(pp.r_smem));
+    const uint64_t desc0 = umma_desc_kmajor_sw128(pp.r_smem);
     while (it.next(m_tile, n0, n1)) {
-        mbar_wait(pp.q_full, it.seg & 1);
+        mbar_wait_s(pp.q_full, it.seg & 1);
         tc_fence_after_sync();
         for (int nt = n0; nt < n1; ++nt) {
-            mbar_wait_relaxed(&pp.acc_empty[buf], aphase ^ 1, 32);
+            mbar_wait_relaxed_s(pp.acc_empty + 8 * buf, aphase ^ 1, 32);
             tc_fence_after_sync();
             const uint32_t d_tmem = pp.tmem_base + buf * kTile;
 #pragma unroll
             for (int c = 0; c < Cfg::kChunks; ++c) {
-                mbar_wait(&pp.full[stage], phase);
+                mbar_wait_s(pp.full + 8 * stage, phase);
                 tc_fence_after_sync();
                 if (elect_one()) {
                     // stage s starts s*16 KiB after stage 0: +1024 in the (addr >> 4) field; K-step k: +2
@@ -127,15 +129,15 @@ __device__ __forceinline__ void idx_role_mma(const IdxPipe& pp, const AffinityPa
                         for (int k = 0; k < kKC / 16; ++k)
                             umma_bf16_ts(d_tmem, q_hi + (c * 4 + k) * 8, b_desc + 2 * k, idesc, (c | k) != 0);
                     }
-                    umma_commit(&pp.empty[stage]);
-                    if (c == Cfg::kChunks - 1) umma_commit(&pp.acc_full[buf]);
+                    umma_commit_s(pp.empty + 8 * stage);
+                    if (c == Cfg::kChunks - 1) umma_commit_s(pp.acc_full + 8 * buf);
                 }
                 __syncwarp();
                 if (++stage == kIdxStages) { stage = 0; phase ^= 1; }
             }
             if (++buf == Cfg::kAccBufs) { buf = 0; aphase ^= 1; }
         }
-        if (elect_one()) umma_commit(pp.q_empty);
+        if (elect_one()) umma_commit_s(pp.q_empty);
         __syncwarp();
     }
 }
@@ -148,7 +150,7 @@ __device__ __forceinline__ void idx_stage_target(const IdxPipe& pp, const Affini
                                                  int row, uint32_t lane_base, int sub, int n_sub) {
     using Cfg = IdxCfg<kSplit>;
     if (seg > 0) {
-        mbar_wait(pp.q_empty, (seg - 1) & 1);
+        mbar_wait_s(pp.q_empty, (seg - 1) & 1);
         tc_fence_after_sync();
     }
     const size_t q_row = (static_cast<size_t>(prm.q_slot) * prm.p_pad + m_tile * kTile + row) * kK;
@@ -166,37 +168,39 @@ __device__ __forceinline__ void idx_stage_target(const IdxPipe& pp, const Affini
     }
     tmem_st_wait();
     tc_fence_before_sync();
-    mbar_arrive(pp.q_full);
+    mbar_arrive_s(pp.q_full);
 }
 
 __device__ __forceinline__ IdxPipe idx_setup(uint8_t* smem_raw, const CUtensorMap* tmap_hi, const CUtensorMap* tmap_lo,
                                              int n_acc_bufs, int epi_threads) {
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     IdxPipe pp;
-    pp.r_smem = smem;                                   // kIdxStages x 16 KiB
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kIdxStages * kChunkBytes);
-    pp.full = bars;                              // [kIdxStages] TMA -> MMA
-    pp.empty = pp.full + kIdxStages;             // [kIdxStages] MMA -> TMA
-    pp.q_full = pp.empty + kIdxStages;           // epilogue threads -> MMA : target tile is in TMEM
-    pp.q_empty = pp.q_full + 1;                  // MMA -> epilogue : target tile may be replaced
-    pp.acc_full = pp.q_empty + 1;                // [kIdxMaxAccBufs] MMA -> epilogue
-    pp.acc_empty = pp.acc_full + kIdxMaxAccBufs; // [kIdxMaxAccBufs] epilogue -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pp.acc_empty + kIdxMaxAccBufs);
+    pp.r_smem = base;
+    pp.full = base + kIdxStages * kChunkBytes;
+    pp.empty = pp.full + 8 * kIdxStages;
+    pp.q_full = pp.empty + 8 * kIdxStages;
+    pp.q_empty = pp.q_full + 8;
+    pp.acc_full = pp.q_empty + 8;
+    pp.acc_empty = pp.acc_full + 8 * kIdxMaxAccBufs;
+    const uint32_t tmem_slot = pp.acc_empty + 8 * kIdxMaxAccBufs;
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         prefetch_tmap(tmap_hi);
         prefetch_tmap(tmap_lo);
-        for (int i = 0; i < kIdxStages; ++i) { mbar_init(&pp.full[i], 1); mbar_init(&pp.empty[i], 1); }
-        mbar_init(pp.q_full, epi_threads);
-        mbar_init(pp.q_empty, 1);
-        for (int i = 0; i < n_acc_bufs; ++i) { mbar_init(&pp.acc_full[i], 1); mbar_init(&pp.acc_empty[i], epi_threads); }
+        for (int i = 0; i < kIdxStages; ++i) { mbar_init_s(pp.full + 8 * i, 1); mbar_init_s(pp.empty + 8 * i, 1); }
+        mbar_init_s(pp.q_full, epi_threads);
+        mbar_init_s(pp.q_empty, 1);
+        for (int i = 0; i < n_acc_bufs; ++i) { mbar_init_s(pp.acc_full + 8 * i, 1); mbar_init_s(pp.acc_empty + 8 * i, epi_threads); }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
-    pp.tmem_base = *tmem_slot;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pp.tmem_base) : "r"(tmem_slot) : "memory");
     return pp;
 }
 
@@ -212,11 +216,6 @@ __device__ __forceinline__ void idx_teardown(const IdxPipe& pp) {
 // ------------------------------------------------------------------------------------------------
 // Epilogue arithmetic
 // ------------------------------------------------------------------------------------------------
-struct ChunkGeom {
-    float drc;   // (n_c - m) / W : row-coordinate difference of the step's first column (fractional rows)
-    float bx;    // x(n_c) - x(m)  : column difference of the step's first column
-    int jw;      // first column of the step that belongs to the next image row (>= kQC: none)
-};
 
 // alpha + beta*j + gamma*j^2 = -coef*((drc + j/W)^2 + (bx + j)^2); `shift` is folded into alpha
 __device__ __forceinline__ void quad_coeffs(float drc, float bx, float inv_w, float coef, float shift, float& alpha, float& beta) {
@@ -243,7 +242,7 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, float (&v)[16
         : "memory");
 }
 
-constexpr int kQC = 16;   // columns per epilogue step (kept small: the three unrolled paths must fit the I-cache)
+constexpr int kQC = 16;   // columns per epilogue step
 
 __device__ __forceinline__ float max16(const float (&v)[kQC]) {
     const float a = fmax3(v[0], v[1], v[2]), b = fmax3(v[3], v[4], v[5]), c = fmax3(v[6], v[7], v[8]);
@@ -251,27 +250,27 @@ __device__ __forceinline__ float max16(const float (&v)[kQC]) {
     return fmax3(fmax3(a, b, c), fmax3(d, e, v[15]), a);
 }
 
-// One 16-column step of one target pixel.  cls_lane: class byte of column (lane - lane_shift) for the 16
-// lanes [lane_shift, lane_shift+16).  n_valid: valid leading columns (>= 16 unless the tile is ragged).
-// Arithmetic per column j:  p = 2^(s*scale2 - m) ;  l += p ;  acc[class(j)] += p * 2^(alpha + beta*j + gamma*j^2)
-// in packed fp32 pairs (FFMA2/FMUL2/FADD2).
+// Per-reference-frame constants of the prior (warp-uniform)
+struct PriorConst {
+    float coef;    // log2(e) / sigma^2   (0: no prior)
+    float gamma;   // -coef * (1 + 1/W^2)
+    float k8;      // 2^(8*gamma)
+    bool chain_always;   // the recurrence of step16_chain is safe for every (target, reference) pair of this frame
+};
+__device__ __forceinline__ PriorConst prior_const(float coef, float inv_w, float w_lowres, float h_lowres) {
+    PriorConst pc;
+    pc.coef = coef;
+    pc.gamma = -coef * fmaf(inv_w, inv_w, 1.0f);
+    pc.k8 = ex2(8.f * pc.gamma);
+    // |beta| <= 2*coef*(|drc|/W + |bx|) <= 2*coef*(H_d/W + W): exponent spread inside a 16-column step
+    pc.chain_always = fmaf(30.f * coef, fmaf(h_lowres, inv_w, w_lowres), -225.f * pc.gamma) < 100.f;
+    return pc;
+}
+
+// Running softmax maximum of one target pixel: fold in the 16 new logits, rescale the sums when it moves.
 template <int D>
-__device__ __forceinline__ void consume16_idx(RowAcc<D>& st, float (&v)[kQC], uint32_t cls_lane, int lane_shift,
-                                              int n_valid, const ChunkGeom& g, float inv_w, float coef, float gamma,
-                                              float k8, float scale2, float w_lowres) {
-    const uint32_t full = 0xffffffffu;
-    const uint32_t window = 0xffffu << lane_shift;
-    const bool partial = n_valid < kQC;
-    const uint32_t valid = partial ? (n_valid <= 0 ? 0u : ((1u << n_valid) - 1u)) : 0xffffu;
-    const uint32_t first = __shfl_sync(full, cls_lane, lane_shift);
-    const bool homog = !partial && ((__ballot_sync(full, cls_lane == first) & window) == window);
-    if (partial) {
-#pragma unroll
-        for (int j = 0; j < kQC; ++j)
-            if (!((valid >> j) & 1u)) v[j] = -INFINITY;
-    }
-    const float cmax = max16(v);
-    const float m_new = fmaxf(st.m, cmax * scale2);
+__device__ __forceinline__ void update_max(RowAcc<D>& st, const float (&v)[kQC], float scale2) {
+    const float m_new = fmaxf(st.m, max16(v) * scale2);
     if (m_new > st.m) {
         const float corr = ex2(st.m - m_new);
         st.l *= corr;
@@ -279,116 +278,112 @@ __device__ __forceinline__ void consume16_idx(RowAcc<D>& st, float (&v)[kQC], ui
         for (int c = 0; c < D; ++c) st.acc[c] *= corr;
         st.m = m_new;
     }
+}
+
+// ---- Fast step: 16 consecutive reference pixels on one image row, prior by recurrence.
+// Per column j:  p = 2^(s*scale2 - m) ;  l += p ;  v[j] <- p * g(j)   (returns 2^sh: the factor still missing from v[])
+//   g(j) = 2^(t_j - sh),  t_j = a0 + b0*j + gamma*j^2 = -coef*((dn + j)^2/W^2 + (bx + j)^2)   (predict.py:158-175),
+// carried on column pairs by  G = (g(j), g(j+1)),  G *= Rho,  Rho *= (k8, k8),  Rho = (g(j+2)/g(j), g(j+3)/g(j+1)):
+// five exp2 per step for the prior instead of one per column (relative drift <= ~2e-6 over the 7 steps).
+// `ok` = this lane may use the recurrence (see chain_safe); lanes with ok == false (whole step underflows) get zeros.
+template <int D>
+__device__ __forceinline__ float step16_chain(RowAcc<D>& st, float (&v)[kQC], float a0, float b0, float sh, bool live,
+                                              const PriorConst& pc, float scale2, float& sum) {
     const float neg_m = -st.m;
     const float2 s2 = make_float2(scale2, scale2);
     const float2 nm2 = make_float2(neg_m, neg_m);
+    float2 G = make_float2(0.f, 0.f), Rho = make_float2(0.f, 0.f);
+    float scale = 0.f;
+    if (live) {
+        const float a1 = a0 - sh;
+        const float r0 = fmaf(4.f, pc.gamma, 2.f * b0);                 // log2 rho(0) = 2*beta + 4*gamma
+        G = make_float2(ex2(a1), ex2(a1 + b0 + pc.gamma));
+        Rho = make_float2(ex2(r0), ex2(fmaf(4.f, pc.gamma, r0)));
+        scale = ex2(sh);
+    }
+    const float2 K8 = make_float2(pc.k8, pc.k8);
     float2 l2 = make_float2(0.f, 0.f), sum2 = make_float2(0.f, 0.f);
-    // prior exponent (log2) of column j: t_j = a0 + b0*j + gamma*j^2 (concave); sh = max(t_0, t_15)
-    float a0, b0;
-    quad_coeffs(g.drc, g.bx, inv_w, coef, 0.f, a0, b0);
-    const float sh = fmaxf(a0, fmaf(15.f, b0, fmaf(225.f, gamma, a0)));
-    // the vertex exceeds the end points by < 57*|gamma|: below 2^-150 every weight of the step is 0 in fp32
-    // (as is exp(-d^2/sigma^2) in the reference, predict.py:173)
-    const bool far = fmaf(-57.f, gamma, sh) < -150.f;
-    // exponent spread inside the step < 100: the recurrence below cannot cross an underflow
-    const bool chain_ok = fmaf(fabsf(b0), 15.f, -225.f * gamma) < 100.f;
-    if (homog && g.jw >= kQC && (far || chain_ok)) {
-        // ---- path A: one class, no row wrap.  The prior g(j) = 2^(t_j - sh) is carried on column pairs by
-        //   G = (g(j), g(j+1)),  G *= Rho,  Rho *= (k8, k8),  Rho = (g(j+2)/g(j), g(j+3)/g(j+1)),  k8 = 2^(8*gamma)
-        // five exp2 per step instead of one per column (relative drift <= ~2e-6 over the 7 steps); the step
-        // total is scaled by 2^sh once.
-        float2 G = make_float2(0.f, 0.f), Rho = make_float2(0.f, 0.f);
-        float scale = 0.f;
-        if (!far) {
-            const float a1 = a0 - sh;
-            const float r0 = fmaf(4.f, gamma, 2.f * b0);                    // log2 rho(0) = 2*beta + 4*gamma
-            G = make_float2(ex2(a1), ex2(a1 + b0 + gamma));
-            Rho = make_float2(ex2(r0), ex2(fmaf(4.f, gamma, r0)));
-            scale = ex2(sh);
-        }
-        const float2 K8 = make_float2(k8, k8);
-#pragma unroll
-        for (int j = 0; j < kQC; j += 2) {
-            const float2 e2 = ffma2(make_float2(v[j], v[j + 1]), s2, nm2);
-            const float2 p2 = make_float2(ex2(e2.x), ex2(e2.y));
-            l2 = fadd2(l2, p2);
-            sum2 = ffma2(p2, G, sum2);
-            if (j + 2 < kQC) {
-                G = fmul2(G, Rho);
-                Rho = fmul2(Rho, K8);
-            }
-        }
-        st.l += l2.x + l2.y;
-        add_to_class<D>(st, static_cast<int>(first), (sum2.x + sum2.y) * scale);
-        return;
-    }
-    const float2 g2 = make_float2(gamma, gamma);
-    float aA, bA, aB, bB;
-    quad_coeffs(g.drc, g.bx, inv_w, coef, neg_m, aA, bA);              // alpha already contains -m
-    quad_coeffs(g.drc, g.bx - w_lowres, inv_w, coef, neg_m, aB, bB);   // columns >= jw: next image row
-    if (homog) {
-        // ---- path B: one class, row wrap inside the step
-#pragma unroll
-        for (int j = 0; j < kQC; j += 2) {
-            const bool w0 = j >= g.jw, w1 = j + 1 >= g.jw;
-            const float2 v2 = make_float2(v[j], v[j + 1]);
-            const float2 e2 = ffma2(v2, s2, nm2);
-            float2 t2 = ffma2(make_float2(w0 ? bB : bA, w1 ? bB : bA), make_float2(float(j), float(j + 1)),
-                              make_float2(w0 ? aB : aA, w1 ? aB : aA));
-            t2 = ffma2(g2, make_float2(float(j * j), float((j + 1) * (j + 1))), t2);
-            const float2 u2 = ffma2(v2, s2, t2);
-            l2 = fadd2(l2, make_float2(ex2(e2.x), ex2(e2.y)));
-            sum2 = fadd2(sum2, make_float2(ex2(u2.x), ex2(u2.y)));
-        }
-        st.l += l2.x + l2.y;
-        add_to_class<D>(st, static_cast<int>(first), sum2.x + sum2.y);
-        return;
-    }
-    // ---- path C: mixed classes and/or ragged tile.  Classes >= 1 get predicated adds; class 0 receives
-    // the remainder of the step total (exact up to one rounding of the total).
-    uint32_t mask[D];
-    float part[D];
-#pragma unroll
-    for (int c = 1; c < D; ++c) {
-        mask[c] = (__ballot_sync(full, cls_lane == static_cast<uint32_t>(c)) >> lane_shift) & valid;
-        part[c] = 0.f;
-    }
 #pragma unroll
     for (int j = 0; j < kQC; j += 2) {
-        const bool w0 = j >= g.jw, w1 = j + 1 >= g.jw;
-        const float2 v2 = make_float2(v[j], v[j + 1]);
-        float2 e2 = ffma2(v2, s2, nm2);
-        float2 t2 = ffma2(make_float2(w0 ? bB : bA, w1 ? bB : bA), make_float2(float(j), float(j + 1)),
-                          make_float2(w0 ? aB : aA, w1 ? aB : aA));
-        t2 = ffma2(g2, make_float2(float(j * j), float((j + 1) * (j + 1))), t2);
-        float2 u2 = ffma2(v2, s2, t2);
-        if (partial) {   // padding columns: weight exactly 0 in both sums
-            if (!((valid >> j) & 1u)) { e2.x = -INFINITY; u2.x = -INFINITY; }
-            if (!((valid >> (j + 1)) & 1u)) { e2.y = -INFINITY; u2.y = -INFINITY; }
-        }
-        l2 = fadd2(l2, make_float2(ex2(e2.x), ex2(e2.y)));
-        const float pw0 = ex2(u2.x), pw1 = ex2(u2.y);
-        sum2 = fadd2(sum2, make_float2(pw0, pw1));
-#pragma unroll
-        for (int c = 1; c < D; ++c) {
-            if ((mask[c] >> j) & 1u) part[c] += pw0;
-            if ((mask[c] >> (j + 1)) & 1u) part[c] += pw1;
+        const float2 e2 = ffma2(make_float2(v[j], v[j + 1]), s2, nm2);
+        const float2 p2 = make_float2(ex2(e2.x), ex2(e2.y));
+        l2 = fadd2(l2, p2);
+        const float2 pw2 = fmul2(p2, G);
+        sum2 = fadd2(sum2, pw2);
+        v[j] = pw2.x;
+        v[j + 1] = pw2.y;
+        if (j + 2 < kQC) {
+            G = fmul2(G, Rho);
+            Rho = fmul2(Rho, K8);
         }
     }
     st.l += l2.x + l2.y;
-    float rest = sum2.x + sum2.y;
+    sum = sum2.x + sum2.y;
+    return scale;
+}
+
+// ---- Generic step: row wrap inside the step (columns >= jw are on the next image row: bx - W), ragged frame tail
+// (`valid` mask), or a prior too steep for the recurrence (tiny sigma).  Every exponent is evaluated directly, the
+// second exp2 per column on the MUFU.  v[j] <- p * prior (complete; factor 1).
+template <int D>
+__device__ __forceinline__ float step16_direct(RowAcc<D>& st, float (&v)[kQC], float drc, float bx, int jw, uint32_t valid,
+                                               const PriorConst& pc, float inv_w, float scale2, float w_lowres, float& sum) {
+    const float neg_m = -st.m;
+    const float2 s2 = make_float2(scale2, scale2);
+    const float2 nm2 = make_float2(neg_m, neg_m);
+    const float2 g2 = make_float2(pc.gamma, pc.gamma);
+    float aA, bA, aB, bB;
+    quad_coeffs(drc, bx, inv_w, pc.coef, neg_m, aA, bA);
+    quad_coeffs(drc, bx - w_lowres, inv_w, pc.coef, neg_m, aB, bB);
+    float2 l2 = make_float2(0.f, 0.f), sum2 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int c = 1; c < D; ++c) {
-        st.acc[c] += part[c];
-        rest -= part[c];
+    for (int j = 0; j < kQC; j += 2) {
+        const bool w0 = j >= jw, w1 = j + 1 >= jw;
+        const float2 v2 = make_float2(v[j], v[j + 1]);      // -inf on padding columns -> both exponentials are 0
+        const float2 e2 = ffma2(v2, s2, nm2);
+        float2 t2 = ffma2(make_float2(w0 ? bB : bA, w1 ? bB : bA), make_float2(float(j), float(j + 1)),
+                          make_float2(w0 ? aB : aA, w1 ? aB : aA));
+        t2 = ffma2(g2, make_float2(float(j * j), float((j + 1) * (j + 1))), t2);
+        const float2 u2 = ffma2(v2, s2, t2);
+        l2 = fadd2(l2, make_float2(ex2(e2.x), ex2(e2.y)));
+        const float2 pw2 = make_float2(ex2(u2.x), ex2(u2.y));
+        sum2 = fadd2(sum2, pw2);
+        v[j] = pw2.x;
+        v[j + 1] = pw2.y;
     }
-    st.acc[0] += fmaxf(rest, 0.f);
+    st.l += l2.x + l2.y;
+    sum = sum2.x + sum2.y;
+    return 1.f;
+}
+
+// Label gather of a class-mixed step: v[] holds the 16 weights (times `scale`), `cls_lane` the class byte of the warp's
+// column `lane` (this step: lanes [lane_shift, +16)), `mk` the columns of class `c` (both warp-uniform).  One pass per
+// class present; the last class receives the remainder of the step total.
+template <int D>
+__device__ __forceinline__ void gather_mixed(RowAcc<D>& st, const float (&v)[kQC], uint32_t cls_lane, int lane_shift,
+                                             uint32_t valid, uint32_t c, uint32_t mk, float sum, float scale) {
+    const uint32_t full = 0xffffffffu;
+    uint32_t rem = valid;
+    float rest = sum;
+    while (true) {
+        rem &= ~mk;
+        if (rem == 0u) break;
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < kQC; ++j)
+            if ((mk >> j) & 1u) s += v[j];
+        add_to_class<D>(st, static_cast<int>(c), s * scale);
+        rest -= s;
+        c = __shfl_sync(full, cls_lane, lane_shift + __ffs(rem) - 1);
+        mk = (__ballot_sync(full, cls_lane == c) >> lane_shift) & rem;
+    }
+    add_to_class<D>(st, static_cast<int>(c), fmaxf(rest, 0.f) * scale);
 }
 
 template <int D, bool kSplit>
 __global__ void __launch_bounds__(kIdxThreads, 1)
 vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
-                 const AffinityParams prm) {
+                 const __grid_constant__ AffinityParams prm) {
     using Cfg = IdxCfg<kSplit>;
     extern __shared__ uint8_t smem_raw[];
     const IdxPipe pp = idx_setup(smem_raw, &tmap_hi, &tmap_lo, Cfg::kAccBufs, kIdxEpiThreads);
@@ -402,11 +397,18 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
         idx_role_mma<kSplit>(pp, prm, dec);
     } else {
         // ================= epilogue: warps 2-17; TMEM lanes [32*(warp%4), +32); logit columns [32*sub, +32)
+        const uint32_t full = 0xffffffffu;
         const int quarter = warp & 3;
         const int sub = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
         const int W = prm.w_lowres;
+        const float w_f = static_cast<float>(W);
+        const float h_f = static_cast<float>((prm.n_pixels + W - 1) / W);
+        const float inv_w = prm.inv_w, scale2 = prm.scale2;
+        const int x_step = kTile % W;
+        const int last_valid = prm.n_pixels - (dec.tpf - 1) * kTile - sub * 32;   // real columns of this warp in a frame's last tile
+        const uint32_t ragged = last_valid >= 32 ? 0xffffffffu : (last_valid <= 0 ? 0u : ((1u << last_valid) - 1u));
         vosd::SegIter it(dec, blockIdx.x);
         int m_tile, n0, n1;
         uint32_t buf = 0, aphase = 0;
@@ -420,52 +422,85 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             int r = n0 / dec.tpf;
             int j = n0 - r * dec.tpf;
             int x_sub = (j * kTile + sub * 32) % W;       // image column of this warp's first logit column
-            const int x_step = kTile % W;
-            float coef = prm.ref_coef[r];
-            float gamma = -coef * fmaf(prm.inv_w, prm.inv_w, 1.0f);
-            float k8 = ex2(8.f * gamma);
+            int dn = j * kTile + sub * 32 - m;            // pixel-index difference of that column to the target pixel
+            const uint8_t* cls_p = prm.cls + static_cast<size_t>(prm.ref_slot[r]) * prm.p_pad + j * kTile + sub * 32 + lane;
+            PriorConst pc = prior_const(prm.ref_coef[r], inv_w, w_f, h_f);
             for (int nt = n0; nt < n1; ++nt) {
-                const size_t row0 = static_cast<size_t>(prm.ref_slot[r]) * prm.p_pad + j * kTile + sub * 32;
-                const uint32_t cls_lane = prm.cls[row0 + lane];      // class byte of logit column `lane`
-                const int n_sub = j * kTile + sub * 32;              // pixel index (in its frame) of column 0
-                const int n_valid = min(kTile, prm.n_pixels - j * kTile) - sub * 32;
-                mbar_wait(&pp.acc_full[buf], aphase);
+                const uint32_t cls_lane = __ldg(cls_p);              // class byte of logit column `lane`
+                const uint32_t valid32 = (j == dec.tpf - 1) ? ragged : full;
+                mbar_wait_s(pp.acc_full + 8 * buf, aphase);
                 tc_fence_after_sync();
                 const uint32_t taddr = pp.tmem_base + lane_base + buf * kTile + sub * 32;
-                float v0[kQC], v1[kQC];
-                tmem_ld_32x32b_x16(taddr, v0);
-                tmem_ld_32x32b_x16(taddr + kQC, v1);
-                tmem_ld_wait();
-                tc_fence_before_sync();
-                mbar_arrive(&pp.acc_empty[buf]);                     // this warp's columns are in registers
-                if (++buf == Cfg::kAccBufs) { buf = 0; aphase ^= 1; }
+                const uint32_t cls0 = __shfl_sync(full, cls_lane, 0);
+                const uint32_t same32 = __ballot_sync(full, cls_lane == cls0);
                 int xq = x_sub;
 #pragma unroll 1
                 for (int q = 0; q < 2; ++q) {
-                    ChunkGeom g;
-                    g.drc = static_cast<float>(n_sub + q * kQC - m) * prm.inv_w;
-                    g.bx = static_cast<float>(xq - xm);
-                    g.jw = W - xq;
-                    if (q == 0)
-                        consume16_idx<D>(st, v0, cls_lane, 0, n_valid, g, prm.inv_w, coef, gamma, k8, prm.scale2, static_cast<float>(W));
-                    else
-                        consume16_idx<D>(st, v1, cls_lane, kQC, n_valid - kQC, g, prm.inv_w, coef, gamma, k8, prm.scale2, static_cast<float>(W));
+                    float v[kQC];
+                    tmem_ld_32x32b_x16(taddr + q * kQC, v);
+                    tmem_ld_wait();
+                    if (q == 1) {                                    // both halves of this warp's columns are in registers
+                        tc_fence_before_sync();
+                        mbar_arrive_s(pp.acc_empty + 8 * buf);
+                    }
+                    const int lane_shift = q * kQC;
+                    const uint32_t valid = (valid32 >> lane_shift) & 0xffffu;
+                    const int jw = W - xq;                            // first column of the step on the next image row
+                    const float bx = static_cast<float>(xq - xm);
+                    const float drc = static_cast<float>(dn + lane_shift) * inv_w;
                     xq += kQC;
                     if (xq >= W) xq -= W;
+                    if (valid == 0u) continue;                       // beyond the frame's last pixel
+                    if (valid != 0xffffu) {
+#pragma unroll
+                        for (int i = 0; i < kQC; ++i)
+                            if (!((valid >> i) & 1u)) v[i] = -INFINITY;
+                    }
+                    update_max<D>(st, v, scale2);
+                    float sum, scale;
+                    bool fast = jw >= kQC && valid == 0xffffu;
+                    float a0, b0, sh;
+                    bool live = true;
+                    if (fast) {
+                        // prior exponent (log2) of column i: t_i = a0 + b0*i + gamma*i^2 (concave); sh = max(t_0, t_15)
+                        quad_coeffs(drc, bx, inv_w, pc.coef, 0.f, a0, b0);
+                        sh = fmaxf(a0, fmaf(15.f, b0, fmaf(225.f, pc.gamma, a0)));
+                        if (!pc.chain_always) {
+                            // the vertex exceeds the end points by < 57*|gamma|: below 2^-150 every weight of the step is 0
+                            // in fp32 (as is exp(-d^2/sigma^2) in the reference, predict.py:173) -> dead lane;
+                            // exponent spread inside the step < 100: the recurrence cannot cross an underflow
+                            live = !(fmaf(-57.f, pc.gamma, sh) < -150.f);
+                            const bool chain_ok = fmaf(fabsf(b0), 15.f, -225.f * pc.gamma) < 100.f;
+                            fast = __all_sync(full, !live || chain_ok);
+                        }
+                    }
+                    if (fast) scale = step16_chain<D>(st, v, a0, b0, sh, live, pc, scale2, sum);
+                    else scale = step16_direct<D>(st, v, drc, bx, jw, valid, pc, inv_w, scale2, w_f, sum);
+                    // ---- label gather: add each column's weight to its class (class bytes are warp-uniform per column)
+                    uint32_t c = cls0, mk = same32 & 0xffffu;
+                    if (q == 1 || valid != 0xffffu) {
+                        c = __shfl_sync(full, cls_lane, lane_shift + __ffs(valid) - 1);
+                        mk = (__ballot_sync(full, cls_lane == c) >> lane_shift) & valid;
+                    }
+                    if (mk == valid) add_to_class<D>(st, static_cast<int>(c), sum * scale);   // one class (common)
+                    else gather_mixed<D>(st, v, cls_lane, lane_shift, valid, c, mk, sum, scale);
                 }
+                if (++buf == Cfg::kAccBufs) { buf = 0; aphase ^= 1; }
                 // next tile: 128 pixels further in the same frame, or tile 0 of the next reference frame
                 if (++j == dec.tpf) {
                     j = 0;
                     ++r;
                     x_sub = (sub * 32) % W;
+                    dn = sub * 32 - m;
                     if (nt + 1 < n1) {
-                        coef = prm.ref_coef[r];
-                        gamma = -coef * fmaf(prm.inv_w, prm.inv_w, 1.0f);
-                        k8 = ex2(8.f * gamma);
+                        pc = prior_const(prm.ref_coef[r], inv_w, w_f, h_f);
+                        cls_p = prm.cls + static_cast<size_t>(prm.ref_slot[r]) * prm.p_pad + sub * 32 + lane;
                     }
                 } else {
                     x_sub += x_step;
                     if (x_sub >= W) x_sub -= W;
+                    dn += kTile;
+                    cls_p += kTile;
                 }
             }
             float* rec = prm.partials +

@@ -476,35 +476,50 @@ __device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
     return min(static_cast<int>(floorf(static_cast<float>(dst) * scale)), in_size - 1);
 }
 
-__global__ void __launch_bounds__(128) vos_merge_writeback(const MergeParams prm) {
+constexpr int kMergeThreads = 1024;   // 128 pixel groups of 8 lanes
+constexpr int kMergeLanes = 8;        // lanes cooperating on one target pixel
+
+__global__ void __launch_bounds__(kMergeThreads) vos_merge_writeback(const MergeParams prm) {
     extern __shared__ uint8_t row_cls[];  // [w_lowres]
     const int y = blockIdx.x;
     const vosd::Decomp dec = vosd::make_decomp(prm.n_pixels, prm.n_refs, prm.num_sms);
-    for (int x = threadIdx.x; x < prm.w_lowres; x += blockDim.x) {
+    const int sublane = threadIdx.x & (kMergeLanes - 1);
+    const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~(kMergeLanes - 1));   // the 8 lanes of this pixel group
+    for (int x = threadIdx.x / kMergeLanes; x < prm.w_lowres; x += kMergeThreads / kMergeLanes) {
         const int pix = y * prm.w_lowres + x;
         const int mt = pix / kTile, row = pix % kTile;
         const int64_t lin_lo = static_cast<int64_t>(mt) * dec.nt;
         const int c_first = vosd::cta_of(dec, lin_lo), c_last = vosd::cta_of(dec, lin_lo + dec.nt - 1);
-        float M = kNegBig;
-        for (int c = c_first; c <= c_last; ++c) {
-            const int seg = mt - static_cast<int>(vosd::cta_begin(dec, c) / dec.nt);
-            const float* rec = prm.partials + (static_cast<size_t>(c * dec.max_segs + seg) * prm.n_sub) * kPartFloats;
-            for (int h = 0; h < prm.n_sub; ++h) M = fmaxf(M, rec[h * kPartFloats + row]);
-        }
-        float L = 0.f, acc[kMaxClasses];
+        const int n_rec = (c_last - c_first + 1) * prm.n_sub;
+        // each lane folds records sublane, sublane+8, ... (online softmax merge), then an 8-lane butterfly
+        float M = kNegBig, L = 0.f, acc[kMaxClasses];
 #pragma unroll
         for (int k = 0; k < kMaxClasses; ++k) acc[k] = 0.f;
-        for (int c = c_first; c <= c_last; ++c) {
+        for (int i = sublane; i < n_rec; i += kMergeLanes) {
+            const int c = c_first + i / prm.n_sub, h = i % prm.n_sub;
             const int seg = mt - static_cast<int>(vosd::cta_begin(dec, c) / dec.nt);
-            for (int h = 0; h < prm.n_sub; ++h) {
-                const float* rec = prm.partials + (static_cast<size_t>(c * dec.max_segs + seg) * prm.n_sub + h) * kPartFloats;
-                const float wgt = vosptx::ex2(rec[row] - M);
-                L = fmaf(rec[kTile + row], wgt, L);
+            const float* rec = prm.partials + (static_cast<size_t>(c * dec.max_segs + seg) * prm.n_sub + h) * kPartFloats;
+            const float m_r = rec[row];
+            const float M_new = fmaxf(M, m_r);
+            const float w_old = vosptx::ex2(M - M_new), w_new = vosptx::ex2(m_r - M_new);
+            L = fmaf(rec[kTile + row], w_new, L * w_old);
 #pragma unroll
-                for (int k = 0; k < kMaxClasses; ++k)
-                    if (k < prm.d) acc[k] = fmaf(rec[(2 + k) * kTile + row], wgt, acc[k]);
-            }
+            for (int k = 0; k < kMaxClasses; ++k)
+                if (k < prm.d) acc[k] = fmaf(rec[(2 + k) * kTile + row], w_new, acc[k] * w_old);
+            M = M_new;
         }
+#pragma unroll
+        for (int off = 1; off < kMergeLanes; off <<= 1) {
+            const float M_o = __shfl_xor_sync(gmask, M, off);
+            const float M_new = fmaxf(M, M_o);
+            const float w_a = vosptx::ex2(M - M_new), w_b = vosptx::ex2(M_o - M_new);
+            L = fmaf(__shfl_xor_sync(gmask, L, off), w_b, L * w_a);
+#pragma unroll
+            for (int k = 0; k < kMaxClasses; ++k)
+                if (k < prm.d) acc[k] = fmaf(__shfl_xor_sync(gmask, acc[k], off), w_b, acc[k] * w_a);
+            M = M_new;
+        }
+        if (sublane != 0) continue;
         const float inv = 1.0f / L;
         int best = 0;
         float best_v = -INFINITY;
@@ -534,10 +549,11 @@ __global__ void __launch_bounds__(128) vos_merge_writeback(const MergeParams prm
     // full-res rows that sample low-res row y: a window around y/sy, filtered by the exact rule
     const int guess = static_cast<int>(static_cast<float>(y) / sy);
     const int span = static_cast<int>(1.0f / sy) + 2;
-    for (int dy = max(0, guess - span); dy < min(prm.H, guess + 2 * span); ++dy) {
+    const int dy0 = max(0, guess - span), dy1 = min(prm.H, guess + 2 * span);
+    for (int i = threadIdx.x; i < (dy1 - dy0) * prm.W; i += kMergeThreads) {
+        const int dy = dy0 + i / prm.W, dx = i % prm.W;
         if (nearest_src(dy, sy, prm.h_lowres) != y) continue;
-        uint8_t* out = prm.out_mask_fullres + static_cast<size_t>(dy) * prm.W;
-        for (int dx = threadIdx.x; dx < prm.W; dx += blockDim.x) out[dx] = row_cls[nearest_src(dx, sx, prm.w_lowres)];
+        prm.out_mask_fullres[static_cast<size_t>(dy) * prm.W + dx] = row_cls[nearest_src(dx, sx, prm.w_lowres)];
     }
 }
 

@@ -67,6 +67,55 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
     }
 }
 
+// ---- the same on 32-bit shared-window addresses (kept in registers once, no generic->shared conversion per use)
+__device__ __forceinline__ void mbar_init_s(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_s(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded like mbar_wait, but the bound is a poll count (each try_wait suspends for a hardware time slice),
+// so the spin body is three instructions.
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_s(bar, parity)) return;
+    uint32_t polls = 0;
+    while (!mbar_try_wait_s(bar, parity)) {
+        if (++polls > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_wait_relaxed_s(uint32_t bar, uint32_t parity, uint32_t ns) {
+    if (mbar_try_wait_s(bar, parity)) return;
+    uint32_t polls = 0;
+    while (!mbar_try_wait_s(bar, parity)) {
+        __nanosleep(ns);
+        if (++polls > (1u << 25)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d_s(uint32_t dst, const void* tmap, int x, int y, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_s(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

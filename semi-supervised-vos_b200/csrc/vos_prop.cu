@@ -383,7 +383,7 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     mp.out_prediction = s->out_prediction; mp.out_mask_lowres = s->out_mask_lowres; mp.out_mask_fullres = s->out_mask_fullres;
     {
         TimedLaunch timed(e, VOSPROP_T_MERGE, st);
-        vosk::vos_merge_writeback<<<e->H_d, 128, e->W_d, st>>>(mp);
+        vosk::vos_merge_writeback<<<e->H_d, vosk::kMergeThreads, e->W_d, st>>>(mp);
     }
     VOS_CUDA(cudaGetLastError());
     if (s->write_labels) e->slot_labels[q_slot] = s->probability_propagation ? 2 : 1;
