@@ -24,6 +24,7 @@ extern "C" {
 #define VOSPROP_MAX_CLASSES 14  /* d = objects + 1 (DAVIS <= 11, YouTube-VOS <= 11)            */
 #define VOSPROP_FEAT_DIM 256    /* VOSNet embedding width, src/model/vos_net.py:22             */
 #define VOSPROP_TILE 128        /* pixel tile of the affinity kernel                           */
+#define VOSPROP_MAX_TOPK 64     /* largest k of the top-k extension                            */
 
 enum vosprop_status {
     VOSPROP_OK = 0,
@@ -73,12 +74,15 @@ typedef struct vosprop_step {
     float temperature;                       /* multiplies the logits (predict.py:52); >= 0     */
     int32_t probability_propagation;         /* 1: store raw prediction as the new label (inference_utils.py:67-68) */
     int32_t write_labels;                    /* 1: write the new label into the ring (normal); 0: pure predict()  */
-    int32_t topk;                            /* 0: full softmax (reference); >0: top-k extension */
+    int32_t topk;                            /* 0: full softmax (the reference).  1..VOSPROP_MAX_TOPK: EXTENSION -- the softmax of
+                                                predict.py:55 runs over the k largest logit*temperature per target pixel only
+                                                (ties -> lowest reference index); prior and label gather unchanged            */
     int32_t kernel;                          /* enum vosprop_kernel                             */
     float* out_prediction;                   /* device (d, P) fp32 or NULL  -- predict()'s return value */
     uint8_t* out_mask_lowres;                /* device (P) uint8 or NULL    -- argmax over d at stride 8 */
     uint8_t* out_mask_fullres;               /* device (H, W) uint8 or NULL -- nearest up-sample + argmax (inference_utils.py:74-75) */
-    int32_t* out_topk_idx;                   /* device (P, topk) int32 or NULL (top-k mode only) */
+    int32_t* out_topk_idx;                   /* device (P, topk) int32 or NULL (top-k mode only): reference indices r*P + pixel
+                                                (r = position in ref_frames), best first; -1 where fewer than k exist         */
 } vosprop_step;
 
 const char* vosprop_last_error(void);

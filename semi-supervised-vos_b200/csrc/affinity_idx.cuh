@@ -58,7 +58,7 @@ struct IdxPipe {              // 32-bit shared-window addresses, computed once p
 // TMA producer (one warp): kChunks reference chunks per tile through the kIdxStages ring.
 // The whole warp walks the (uniform) control flow; elect.sync picks the issuing lane, which lets
 // ptxas keep addresses in uniform registers instead of a per-instruction waterfall.
-template <bool kSplit>
+template <bool kSplit, int kStages>
 __device__ __forceinline__ void idx_role_producer(const IdxPipe& pp, const CUtensorMap* tmap_hi, const CUtensorMap* tmap_lo,
                                                   const AffinityParams& prm, const vosd::Decomp& dec) {
     constexpr int kChunks = IdxCfg<kSplit>::kChunks;
@@ -80,14 +80,14 @@ __device__ __forceinline__ void idx_role_producer(const IdxPipe& pp, const CUten
                         tma_load_2d_s(pp.r_smem + stage * kChunkBytes, tmap_hi, c * kKC, row0, pp.full + 8 * stage);
                 }
                 __syncwarp();
-                if (++stage == kIdxStages) { stage = 0; phase ^= 1; }
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     }
 }
 
 // MMA issuer (one warp, one elected lane issues): D[tmem] += Q[tmem] . R[smem]^T
-template <bool kSplit>
+template <bool kSplit, int kStages>
 __device__ __forceinline__ void idx_role_mma(const IdxPipe& pp, const AffinityParams& prm, const vosd::Decomp& dec) {
     using Cfg = IdxCfg<kSplit>;
     const uint32_t idesc = prm.idesc;
@@ -133,7 +133,7 @@ __device__ __forceinline__ void idx_role_mma(const IdxPipe& pp, const AffinityPa
                     if (c == Cfg::kChunks - 1) umma_commit_s(pp.acc_full + 8 * buf);
                 }
                 __syncwarp();
-                if (++stage == kIdxStages) { stage = 0; phase ^= 1; }
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
             if (++buf == Cfg::kAccBufs) { buf = 0; aphase ^= 1; }
         }
@@ -171,14 +171,15 @@ __device__ __forceinline__ void idx_stage_target(const IdxPipe& pp, const Affini
     mbar_arrive_s(pp.q_full);
 }
 
+template <int kStages>
 __device__ __forceinline__ IdxPipe idx_setup(uint8_t* smem_raw, const CUtensorMap* tmap_hi, const CUtensorMap* tmap_lo,
                                              int n_acc_bufs, int epi_threads) {
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     IdxPipe pp;
     pp.r_smem = base;
-    pp.full = base + kIdxStages * kChunkBytes;
-    pp.empty = pp.full + 8 * kIdxStages;
-    pp.q_full = pp.empty + 8 * kIdxStages;
+    pp.full = base + kStages * kChunkBytes;
+    pp.empty = pp.full + 8 * kStages;
+    pp.q_full = pp.empty + 8 * kStages;
     pp.q_empty = pp.q_full + 8;
     pp.acc_full = pp.q_empty + 8;
     pp.acc_empty = pp.acc_full + 8 * kIdxMaxAccBufs;
@@ -187,7 +188,7 @@ __device__ __forceinline__ IdxPipe idx_setup(uint8_t* smem_raw, const CUtensorMa
     if (threadIdx.x == 0) {
         prefetch_tmap(tmap_hi);
         prefetch_tmap(tmap_lo);
-        for (int i = 0; i < kIdxStages; ++i) { mbar_init_s(pp.full + 8 * i, 1); mbar_init_s(pp.empty + 8 * i, 1); }
+        for (int i = 0; i < kStages; ++i) { mbar_init_s(pp.full + 8 * i, 1); mbar_init_s(pp.empty + 8 * i, 1); }
         mbar_init_s(pp.q_full, epi_threads);
         mbar_init_s(pp.q_empty, 1);
         for (int i = 0; i < n_acc_bufs; ++i) { mbar_init_s(pp.acc_full + 8 * i, 1); mbar_init_s(pp.acc_empty + 8 * i, epi_threads); }
@@ -386,15 +387,15 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                  const __grid_constant__ AffinityParams prm) {
     using Cfg = IdxCfg<kSplit>;
     extern __shared__ uint8_t smem_raw[];
-    const IdxPipe pp = idx_setup(smem_raw, &tmap_hi, &tmap_lo, Cfg::kAccBufs, kIdxEpiThreads);
+    const IdxPipe pp = idx_setup<kIdxStages>(smem_raw, &tmap_hi, &tmap_lo, Cfg::kAccBufs, kIdxEpiThreads);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const vosd::Decomp dec = vosd::make_decomp(prm.n_pixels, prm.n_refs, prm.num_sms);
 
     if (warp == 0) {
-        idx_role_producer<kSplit>(pp, &tmap_hi, &tmap_lo, prm, dec);
+        idx_role_producer<kSplit, kIdxStages>(pp, &tmap_hi, &tmap_lo, prm, dec);
     } else if (warp == 1) {
-        idx_role_mma<kSplit>(pp, prm, dec);
+        idx_role_mma<kSplit, kIdxStages>(pp, prm, dec);
     } else {
         // ================= epilogue: warps 2-17; TMEM lanes [32*(warp%4), +32); logit columns [32*sub, +32)
         const uint32_t full = 0xffffffffu;

@@ -62,6 +62,12 @@ struct AffinityParams {
     float inv_w;          // 1 / W_d
     uint32_t idesc;       // tcgen05 instruction descriptor (f16 or bf16 operands, fp32 accumulate, 128x128)
     int32_t feat_fmt;     // kFmtSplit: ring_hi/ring_lo = bf16 hi + lo; kFmtF16 / kFmtBF16: ring_hi only, one pass
+    // top-k mode (vos_affinity_topk): per (CTA, segment, target pixel) candidate lists
+    float temperature;    // predict.py:52 -- the selection compares logit * temperature as torch computes it
+    int32_t topk;
+    uint32_t* cand_key;   // [grid * max_segs][128][kTopkMax] order-preserving keys of logit * temperature
+    int32_t* cand_idx;    // same shape: reference index r*P + pixel
+    int32_t* cand_cnt;    // [grid * max_segs][128]
 };
 
 enum : int32_t { kFmtSplit = 0, kFmtF16 = 1, kFmtBF16 = 2 };

@@ -6,6 +6,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -16,6 +17,7 @@
 #include "decompose.h"
 #include "kernels.cuh"
 #include "affinity_idx.cuh"
+#include "affinity_topk.cuh"
 
 static_assert(VOSPROP_PREC_SPLIT3 == vosk::kFmtSplit && VOSPROP_PREC_F16 == vosk::kFmtF16 && VOSPROP_PREC_BF16 == vosk::kFmtBF16,
               "precision enum and ring formats must coincide");
@@ -58,6 +60,11 @@ struct vosprop_engine {
     uint8_t* cls = nullptr;   // class-id ring, [slots * p_pad]
     float* partials = nullptr;
     size_t partial_records = 0;
+    // top-k mode scratch (allocated on first use)
+    uint32_t* cand_key = nullptr;
+    int32_t* cand_idx = nullptr;
+    int32_t* cand_cnt = nullptr;
+    uint8_t* low_scratch = nullptr;   // stride-8 class map when the caller wants only the full-resolution mask
     CUtensorMap tmap_hi{}, tmap_lo{};
     EncodeTiledFn encode = nullptr;
     std::vector<int> slot_frame;
@@ -142,6 +149,75 @@ int check_frame(const vosprop_engine* e, int frame_idx) {
     return VOSPROP_OK;
 }
 
+
+// Top-k extension (not in the reference): fused affinity + streaming top-k, then per-pixel finish, then up-sample.
+int propagate_topk(vosprop_engine* e, const vosprop_step* s, vosk::AffinityParams ap, const vosd::Decomp& dec_in, cudaStream_t st) {
+    // Lists merged per target pixel = CTAs whose ranges intersect one target tile's row of the tile grid.  Small maps
+    // with many references would spread one row over dozens of CTAs: shrink the grid until a row has <= 16 lists.
+    int grid_cap = e->num_sms;
+    {
+        const int64_t min_per_cta = (dec_in.nt + 15) / 16;
+        if (dec_in.total / grid_cap < min_per_cta) grid_cap = static_cast<int>(std::max<int64_t>(1, dec_in.total / min_per_cta));
+    }
+    const vosd::Decomp dec = vosd::make_decomp(e->P, s->n_refs, grid_cap);
+    const int64_t per_cta = dec.total / dec.grid;
+    const int64_t lists = (dec.nt + per_cta - 1) / per_cta + 1;
+    if (lists > vosk::kTopkMaxLists)
+        return fail(VOSPROP_ERR_UNSUPPORTED, "top-k: %lld partial lists per target pixel (max %d)", (long long)lists, vosk::kTopkMaxLists);
+    ap.num_sms = grid_cap;
+    if (!e->cand_key) {
+        const size_t rows = e->partial_records / vosk::kIdxSub * vosk::kTile;
+        cudaError_t a1 = cudaMalloc(&e->cand_key, rows * vosk::kTopkMax * 4);
+        cudaError_t a2 = cudaMalloc(&e->cand_idx, rows * vosk::kTopkMax * 4);
+        cudaError_t a3 = cudaMalloc(&e->cand_cnt, rows * 4);
+        cudaError_t a4 = cudaMalloc(&e->low_scratch, static_cast<size_t>(e->cfg.max_pixels));
+        if (a1 != cudaSuccess || a2 != cudaSuccess || a3 != cudaSuccess || a4 != cudaSuccess)
+            return fail(VOSPROP_ERR_CUDA, "cudaMalloc of the top-k candidate lists failed (%zu rows)", rows);
+    }
+    ap.temperature = s->temperature;
+    ap.topk = s->topk;
+    ap.cand_key = e->cand_key; ap.cand_idx = e->cand_idx; ap.cand_cnt = e->cand_cnt;
+    {
+        TimedLaunch timed(e, VOSPROP_T_AFFINITY, st);
+        if (ap.feat_fmt == vosk::kFmtSplit) {
+            VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_topk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kTopkSmem));
+            vosk::vos_affinity_topk<true><<<dec.grid, vosk::kTopkThreads, vosk::kTopkSmem, st>>>(e->tmap_hi, e->tmap_lo, ap);
+        } else {
+            VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_topk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kTopkSmem));
+            vosk::vos_affinity_topk<false><<<dec.grid, vosk::kTopkThreads, vosk::kTopkSmem, st>>>(e->tmap_hi, e->tmap_lo, ap);
+        }
+        VOS_CUDA(cudaGetLastError());
+    }
+    vosk::TopkFinishParams fp{};
+    vosk::MergeParams& mp = fp.mp;
+    const int q_slot = ap.q_slot;
+    mp.n_pixels = e->P; mp.p_pad = e->p_pad; mp.w_lowres = e->W_d; mp.h_lowres = e->H_d; mp.n_refs = s->n_refs;
+    mp.num_sms = grid_cap; mp.d = e->d; mp.H = e->H; mp.W = e->W; mp.q_slot = q_slot;
+    mp.write_labels = s->write_labels; mp.probability = s->probability_propagation; mp.n_sub = 1;
+    mp.partials = nullptr; mp.meta = e->meta; mp.cls = e->cls;
+    mp.out_prediction = s->out_prediction;
+    mp.out_mask_lowres = s->out_mask_lowres ? s->out_mask_lowres : (s->out_mask_fullres ? e->low_scratch : nullptr);
+    mp.out_mask_fullres = nullptr;
+    fp.topk = s->topk;
+    for (int r = 0; r < s->n_refs; ++r) { fp.ref_slot[r] = ap.ref_slot[r]; fp.ref_coef[r] = ap.ref_coef[r]; }
+    fp.cand_key = e->cand_key; fp.cand_idx = e->cand_idx; fp.cand_cnt = e->cand_cnt;
+    fp.out_topk_idx = s->out_topk_idx;
+    {
+        TimedLaunch timed(e, VOSPROP_T_MERGE, st);
+        VOS_CUDA(cudaFuncSetAttribute(vosk::vos_topk_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kFinishSmem));
+        vosk::vos_topk_finish<<<(e->P + vosk::kFinishWarps - 1) / vosk::kFinishWarps, vosk::kFinishWarps * 32, vosk::kFinishSmem, st>>>(fp);
+        VOS_CUDA(cudaGetLastError());
+        if (s->out_mask_fullres) {
+            vosk::vos_upsample_mask<<<e->H, 256, 0, st>>>(mp.out_mask_lowres, s->out_mask_fullres, e->H_d, e->W_d, e->H, e->W);
+            VOS_CUDA(cudaGetLastError());
+            e->launches++;
+        }
+    }
+    if (s->write_labels) e->slot_labels[q_slot] = s->probability_propagation ? 2 : 1;
+    e->launches += 2;
+    return VOSPROP_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -215,6 +291,10 @@ void vosprop_destroy(vosprop_engine* e) {
     cudaFree(e->meta);
     cudaFree(e->partials);
     cudaFree(e->cls);
+    cudaFree(e->cand_key);
+    cudaFree(e->cand_idx);
+    cudaFree(e->cand_cnt);
+    cudaFree(e->low_scratch);
     for (cudaEvent_t ev : e->ev) cudaEventDestroy(ev);
     delete e;
 }
@@ -328,7 +408,9 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     if (s->n_refs < 1 || s->n_refs > VOSPROP_MAX_REFS) return fail(VOSPROP_ERR_INVALID, "n_refs=%d outside 1..%d", s->n_refs, VOSPROP_MAX_REFS);
     if (!(s->temperature >= 0.f) || !std::isfinite(s->temperature))
         return fail(VOSPROP_ERR_UNSUPPORTED, "temperature %g: only finite temperature >= 0 is supported", (double)s->temperature);
-    if (s->topk != 0) return fail(VOSPROP_ERR_UNSUPPORTED, "top-k mode is not built yet (topk=%d)", s->topk);
+    if (s->topk < 0 || s->topk > VOSPROP_MAX_TOPK)
+        return fail(VOSPROP_ERR_UNSUPPORTED, "topk=%d outside 0..%d (0 = full softmax, the reference)", s->topk, VOSPROP_MAX_TOPK);
+    if (s->out_topk_idx && s->topk == 0) return fail(VOSPROP_ERR_INVALID, "out_topk_idx needs topk > 0");
     if (s->kernel < VOSPROP_KERNEL_TC || s->kernel > VOSPROP_KERNEL_TC_DENSE) return fail(VOSPROP_ERR_INVALID, "unknown kernel %d", s->kernel);
     if (s->out_mask_fullres && static_cast<int64_t>(e->H) * e->W > e->cfg.max_fullres_pixels && e->cfg.max_fullres_pixels > 0)
         return fail(VOSPROP_ERR_UNSUPPORTED, "full-resolution frame larger than configured");
@@ -368,6 +450,7 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     if (static_cast<size_t>(dec.grid) * dec.max_segs * vosk::kIdxSub > e->partial_records)
         return fail(VOSPROP_ERR_UNSUPPORTED, "partial buffer too small (grid %d x segs %d)", dec.grid, dec.max_segs);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (s->topk > 0) return propagate_topk(e, s, ap, dec, st);
     {
         TimedLaunch timed(e, VOSPROP_T_AFFINITY, st);
         rc = dispatch_affinity(e, ap, dec.grid, kernel, st);

@@ -6,6 +6,7 @@ from pathlib import Path
 
 MAX_REFS = 32
 MAX_CLASSES = 14
+MAX_TOPK = 64
 FEAT_DIM = 256
 F32, F16, BF16 = 0, 1, 2
 NCHW, NHWC = 0, 1

@@ -151,7 +151,11 @@ class PropagationEngine:
                   temperature: float = 1.0, probability_propagation: bool = False, write_labels: bool = True,
                   kernel: int = capi.KERNEL_TC, want_prediction: bool = True, want_lowres: bool = True,
                   want_fullres: bool = True, out_fullres: Optional[torch.Tensor] = None,
-                  out_prediction: Optional[torch.Tensor] = None, topk: int = 0) -> Dict[str, torch.Tensor]:
+                  out_prediction: Optional[torch.Tensor] = None, topk: int = 0,
+                  want_topk_idx: bool = False) -> Dict[str, torch.Tensor]:
+        """One propagation step.  topk = 0 is the reference (softmax over every reference pixel); topk = k in
+        1..MAX_TOPK is the top-k extension (softmax over the k largest logits per target pixel), optionally
+        returning the (P, k) reference indices r*P + pixel, best first."""
         H_d, W_d, H, W, d = self.geom
         P = H_d * W_d
         st = capi.Step()
@@ -182,6 +186,12 @@ class PropagationEngine:
             assert full.is_contiguous() and full.dtype == torch.uint8 and full.numel() == H * W
             st.out_mask_fullres = full.data_ptr()
             out['mask'] = full
+        if want_topk_idx:
+            if topk <= 0:
+                raise ValueError('want_topk_idx needs topk > 0')
+            tk = torch.empty((P, topk), dtype=torch.int32, device=self.device)
+            st.out_topk_idx = tk.data_ptr()
+            out['topk_idx'] = tk
         capi.check(self._lib.vosprop_propagate(self._h, C.byref(st), self._stream()))
         return out
 

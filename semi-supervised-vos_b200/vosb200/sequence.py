@@ -52,7 +52,7 @@ def start_sequence(engine: PropagationEngine, first_features: torch.Tensor, firs
 def propagate_clip(engine: PropagationEngine, features: torch.Tensor, first_label_full, sigma_1: float = 8.0,
                    sigma_2: float = 21.0, frame_range: int = 40, ref_num: int = 9, temperature: float = 1.0,
                    probability_propagation: bool = False, kernel: int = capi.KERNEL_TC, d: Optional[int] = None,
-                   return_predictions: bool = False, precision: Optional[int] = None):
+                   return_predictions: bool = False, precision: Optional[int] = None, topk: int = 0):
     """features (T,K,H_d,W_d) on the engine's device -> masks (T-1,H,W) uint8 on device
     (+ predictions (T-1,d,P) fp32 when asked).  No host sync inside."""
     first = torch.as_tensor(np.asarray(first_label_full)) if not torch.is_tensor(first_label_full) else first_label_full
@@ -66,5 +66,5 @@ def propagate_clip(engine: PropagationEngine, features: torch.Tensor, first_labe
         engine.append(t, features[t])
         engine.step(t, frame_range, ref_num, sigma_1, sigma_2, temperature, probability_propagation,
                     kernel=kernel, want_prediction=False, want_lowres=False, want_fullres=False,
-                    out_fullres=masks[t - 1], out_prediction=preds[t - 1] if return_predictions else None)
+                    out_fullres=masks[t - 1], out_prediction=preds[t - 1] if return_predictions else None, topk=topk)
     return (masks, preds) if return_predictions else masks
