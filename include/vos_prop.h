@@ -134,6 +134,13 @@ int vosprop_num_sms(const vosprop_engine* e);
  * fills grid size and per-CTA [begin,end) of the linearised (m_tile, n_tile) space. */
 int vosprop_debug_decompose(int32_t n_pixels, int32_t n_refs, int32_t num_sms, int32_t* grid,
                             int64_t* cta_begin /* num_sms+1 entries or NULL */, int32_t* max_segments);
+/* Development aid for profiling: a bit mask that switches off parts of the fused epilogue (bit 0: all per-step
+ * arithmetic, 1: label gather, 2: prior, 3: running-max update, 4: prior and packed math).  Results are WRONG
+ * with any bit set; production code never calls this (flags start at 0). */
+int vosprop_debug_flags(vosprop_engine* e, int32_t flags);
+/* Development aid: device buffer of num_sms*16 int64 that the fused kernel fills with cycle counters of its role
+ * warps (time in each mbarrier wait); NULL (the default) switches the instrumentation off. */
+int vosprop_debug_clocks(vosprop_engine* e, void* device_buffer);
 /* kernel launches issued by this handle since creation (for bench.py's gpu_launches) */
 int64_t vosprop_launch_count(const vosprop_engine* e);
 

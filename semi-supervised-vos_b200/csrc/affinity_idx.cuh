@@ -24,9 +24,9 @@ constexpr int kIdxEpiWarps = 16;     // 4 per scheduler: each owns 32 TMEM lanes
 constexpr int kIdxEpiThreads = kIdxEpiWarps * 32;
 constexpr int kIdxThreads = 64 + kIdxEpiThreads;   // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue
 constexpr int kIdxSub = 4;           // partial records per (CTA, segment): one per 32-column quarter
-constexpr int kIdxStages = 13;       // 13 x 16 KiB reference chunks in flight
+constexpr int kIdxRingChunks = 12;   // 12 x 16 KiB of reference chunks in flight, grouped into stages (IdxCfg)
 constexpr int kIdxMaxAccBufs = 3;
-constexpr int kIdxSmem = kIdxStages * kChunkBytes + 512 + 1024;
+constexpr int kIdxSmem = kIdxRingChunks * kChunkBytes + 512 + 1024;
 
 // Precision-dependent shape of the pipeline.
 //   kSplit = true : fp32 features stored as bf16 hi + lo; S = Qhi.Rhi + Qlo.Rhi + Qhi.Rlo (3 MMA passes, 8 chunks of
@@ -41,11 +41,13 @@ struct IdxCfg {
     static constexpr int kAccBufs = kSplit ? 2 : 3;
     static constexpr uint32_t kTmemQ = kAccBufs * kTile;       // first TMEM column of the target tile
     static constexpr int kQChunks = kSplit ? 8 : 4;            // 32-column TMEM chunks of the target tile
+    static constexpr int kGroup = kSplit ? 2 : 4;              // chunks per pipeline stage: a hi+lo pair / a whole tile
+    static constexpr int kStages = kIdxRingChunks / kGroup;    // 6 x 32 KiB / 3 x 64 KiB
 };
 
 struct IdxPipe {              // 32-bit shared-window addresses, computed once per thread
-    uint32_t r_smem;          // kIdxStages x 16 KiB reference chunks
-    uint32_t full, empty;     // [kIdxStages] TMA -> MMA, MMA -> TMA
+    uint32_t r_smem;          // kStages stages of kGroup x 16 KiB reference chunks
+    uint32_t full, empty;     // [kStages] TMA -> MMA, MMA -> TMA
     uint32_t q_full, q_empty; // epilogue threads -> MMA (target tile is in TMEM), MMA -> epilogue
     uint32_t acc_full, acc_empty;  // [kIdxMaxAccBufs] MMA -> epilogue, epilogue -> MMA
     uint32_t tmem_base;
@@ -55,82 +57,125 @@ struct IdxPipe {              // 32-bit shared-window addresses, computed once p
 // Roles shared by vos_affinity_idx and vos_affinity_topk
 // ------------------------------------------------------------------------------------------------
 
-// TMA producer (one warp): kChunks reference chunks per tile through the kIdxStages ring.
-// The whole warp walks the (uniform) control flow; elect.sync picks the issuing lane, which lets
-// ptxas keep addresses in uniform registers instead of a per-instruction waterfall.
-template <bool kSplit, int kStages>
+// The reference tiles stream through a ring of kStages stages of kGroup 16-KiB chunks each (one mbarrier round trip
+// per stage).  The first ncu-guided versions used one chunk per stage; the profile of the single-pass kernel showed
+// the MMA-issuing warp itself as the limiter: ~45 dependent instructions per barrier round trip for only 4 UMMAs
+// (1650 cycles per tile with the loads switched off, against 1024 cycles of tensor work).  Grouping a whole tile
+// (fp16: 4 chunks, 16 UMMAs) or a hi+lo pair (split: 2 chunks, 12 UMMAs) per stage amortises the round trip.
+//
+// TMA producer (one warp).  The whole warp walks the (uniform) control flow; elect.sync picks the issuing lane,
+// which lets ptxas keep addresses in uniform registers instead of a per-instruction waterfall.
+template <bool kSplit, int kGroup, int kStages>
 __device__ __forceinline__ void idx_role_producer(const IdxPipe& pp, const CUtensorMap* tmap_hi, const CUtensorMap* tmap_lo,
                                                   const AffinityParams& prm, const vosd::Decomp& dec) {
     constexpr int kChunks = IdxCfg<kSplit>::kChunks;
+    constexpr uint32_t kStageBytes = kGroup * kChunkBytes;
+    static_assert(kChunks % kGroup == 0, "a stage holds whole chunks of one tile");
     vosd::SegIter it(dec, blockIdx.x);
     int m_tile, n0, n1;
     uint32_t stage = 0, phase = 0;
+    long long t_wait = 0, t_begin = clock64();
     while (it.next(m_tile, n0, n1)) {
         for (int nt = n0; nt < n1; ++nt) {
             const int r = nt / dec.tpf;
-            const int row0 = prm.ref_slot[r] * prm.p_pad + (nt - r * dec.tpf) * kTile;
-            for (int c = 0; c < kChunks; ++c) {
+            int row0 = prm.ref_slot[r] * prm.p_pad + (nt - r * dec.tpf) * kTile;
+            if (prm.dbg & 64) row0 = 0;                  // profiling: every CTA streams the same tile
+#pragma unroll
+            for (int g = 0; g < kChunks / kGroup; ++g) {
+                const long long t0 = clock64();
                 mbar_wait_relaxed_s(pp.empty + 8 * stage, phase ^ 1, 64);
+                t_wait += clock64() - t0;
                 if (elect_one()) {
-                    mbar_arrive_expect_tx_s(pp.full + 8 * stage, kChunkBytes);
-                    if (kSplit)
-                        tma_load_2d_s(pp.r_smem + stage * kChunkBytes, (c & 1) ? tmap_lo : tmap_hi, (c >> 1) * kKC, row0,
-                                      pp.full + 8 * stage);
-                    else
-                        tma_load_2d_s(pp.r_smem + stage * kChunkBytes, tmap_hi, c * kKC, row0, pp.full + 8 * stage);
+                    const uint32_t bar = pp.full + 8 * stage;
+                    if (prm.dbg & 128) {                 // profiling: no loads at all (MMA on stale shared memory)
+                        mbar_arrive_s(bar);
+                    } else {
+                        mbar_arrive_expect_tx_s(bar, kStageBytes);
+#pragma unroll
+                        for (int i = 0; i < kGroup; ++i) {
+                            const int c = g * kGroup + i;
+                            const uint32_t dst = pp.r_smem + stage * kStageBytes + i * kChunkBytes;
+                            if (kSplit) tma_load_2d_s(dst, (c & 1) ? tmap_lo : tmap_hi, (c >> 1) * kKC, row0, bar);
+                            else tma_load_2d_s(dst, tmap_hi, c * kKC, row0, bar);
+                        }
+                    }
                 }
                 __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     }
+    if (prm.dbg_clk && (threadIdx.x & 31) == 0) {
+        prm.dbg_clk[blockIdx.x * 16 + 0] = clock64() - t_begin;
+        prm.dbg_clk[blockIdx.x * 16 + 1] = t_wait;
+    }
 }
 
 // MMA issuer (one warp, one elected lane issues): D[tmem] += Q[tmem] . R[smem]^T
-template <bool kSplit, int kStages>
+template <bool kSplit, int kGroup, int kStages>
 __device__ __forceinline__ void idx_role_mma(const IdxPipe& pp, const AffinityParams& prm, const vosd::Decomp& dec) {
     using Cfg = IdxCfg<kSplit>;
+    constexpr uint32_t kStageBytes = kGroup * kChunkBytes;
     const uint32_t idesc = prm.idesc;
     vosd::SegIter it(dec, blockIdx.x);
     int m_tile, n0, n1;
     uint32_t stage = 0, phase = 0, buf = 0, aphase = 0;
     const uint32_t q_hi = pp.tmem_base + Cfg::kTmemQ, q_lo = pp.tmem_base + Cfg::kTmemQ + 128;
     const uint64_t desc0 = umma_desc_kmajor_sw128(pp.r_smem);
+    long long t_q = 0, t_acc = 0, t_full = 0, t_begin = clock64();
+    unsigned long long ns_begin;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_begin));
     while (it.next(m_tile, n0, n1)) {
+        long long t0 = clock64();
         mbar_wait_s(pp.q_full, it.seg & 1);
+        t_q += clock64() - t0;
         tc_fence_after_sync();
         for (int nt = n0; nt < n1; ++nt) {
+            t0 = clock64();
             mbar_wait_relaxed_s(pp.acc_empty + 8 * buf, aphase ^ 1, 32);
+            t_acc += clock64() - t0;
             tc_fence_after_sync();
             const uint32_t d_tmem = pp.tmem_base + buf * kTile;
 #pragma unroll
-            for (int c = 0; c < Cfg::kChunks; ++c) {
+            for (int g = 0; g < Cfg::kChunks / kGroup; ++g) {
+                t0 = clock64();
                 mbar_wait_s(pp.full + 8 * stage, phase);
+                t_full += clock64() - t0;
                 tc_fence_after_sync();
                 if (elect_one()) {
-                    // stage s starts s*16 KiB after stage 0: +1024 in the (addr >> 4) field; K-step k: +2
-                    const uint64_t b_desc = desc0 + static_cast<uint64_t>(stage * (kChunkBytes >> 4));
-                    if (kSplit) {
-                        const int kc = c >> 1;
-                        if ((c & 1) == 0) {   // reference hi chunk: Qhi.Rhi + Qlo.Rhi
+                    // stage s starts s*kStageBytes after stage 0 ((addr >> 4) field); chunk i: +1024; K-step k: +2
+                    const uint64_t s_desc = desc0 + static_cast<uint64_t>(stage * (kStageBytes >> 4));
+#pragma unroll
+                    for (int i = 0; i < kGroup; ++i) {
+                        const int c = g * kGroup + i;
+                        const uint64_t b_desc = s_desc + static_cast<uint64_t>(i * (kChunkBytes >> 4));
+                        if (kSplit) {
+                            const int kc = c >> 1;
+                            if ((c & 1) == 0) {   // reference hi chunk: Qhi.Rhi + Qlo.Rhi
+#pragma unroll
+                                for (int k = 0; k < kKC / 16; ++k)
+                                    umma_bf16_ts(d_tmem, q_hi + (kc * 4 + k) * 8, b_desc + 2 * k, idesc, (c | k) != 0);
+#pragma unroll
+                                for (int k = 0; k < kKC / 16; ++k)
+                                    umma_bf16_ts(d_tmem, q_lo + (kc * 4 + k) * 8, b_desc + 2 * k, idesc, 1);
+                            } else {              // reference lo chunk: Qhi.Rlo
+#pragma unroll
+                                for (int k = 0; k < kKC / 16; ++k)
+                                    umma_bf16_ts(d_tmem, q_hi + (kc * 4 + k) * 8, b_desc + 2 * k, idesc, 1);
+                            }
+                        } else if (prm.dbg & 256) {       // profiling: no tensor work at all
+                        } else if (prm.dbg & 512) {       // profiling: consecutive UMMAs into different accumulators
 #pragma unroll
                             for (int k = 0; k < kKC / 16; ++k)
-                                umma_bf16_ts(d_tmem, q_hi + (kc * 4 + k) * 8, b_desc + 2 * k, idesc, (c | k) != 0);
+                                umma_bf16_ts(pp.tmem_base + ((k & 1) ? 128u : 0u), q_hi + (c * 4 + k) * 8, b_desc + 2 * k, idesc, (c | k) != 0);
+                        } else {
 #pragma unroll
                             for (int k = 0; k < kKC / 16; ++k)
-                                umma_bf16_ts(d_tmem, q_lo + (kc * 4 + k) * 8, b_desc + 2 * k, idesc, 1);
-                        } else {              // reference lo chunk: Qhi.Rlo
-#pragma unroll
-                            for (int k = 0; k < kKC / 16; ++k)
-                                umma_bf16_ts(d_tmem, q_hi + (kc * 4 + k) * 8, b_desc + 2 * k, idesc, 1);
+                                umma_bf16_ts(d_tmem, q_hi + (c * 4 + k) * 8, b_desc + 2 * k, idesc, (c | k) != 0);
                         }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < kKC / 16; ++k)
-                            umma_bf16_ts(d_tmem, q_hi + (c * 4 + k) * 8, b_desc + 2 * k, idesc, (c | k) != 0);
                     }
                     umma_commit_s(pp.empty + 8 * stage);
-                    if (c == Cfg::kChunks - 1) umma_commit_s(pp.acc_full + 8 * buf);
+                    if (g == Cfg::kChunks / kGroup - 1) umma_commit_s(pp.acc_full + 8 * buf);
                 }
                 __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -139,6 +184,17 @@ __device__ __forceinline__ void idx_role_mma(const IdxPipe& pp, const AffinityPa
         }
         if (elect_one()) umma_commit_s(pp.q_empty);
         __syncwarp();
+    }
+    if (prm.dbg_clk && (threadIdx.x & 31) == 0) {
+        prm.dbg_clk[blockIdx.x * 16 + 2] = clock64() - t_begin;
+        prm.dbg_clk[blockIdx.x * 16 + 3] = t_q;
+        prm.dbg_clk[blockIdx.x * 16 + 4] = t_acc;
+        prm.dbg_clk[blockIdx.x * 16 + 5] = t_full;
+        unsigned long long ns_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_end));
+        prm.dbg_clk[blockIdx.x * 16 + 6] = static_cast<long long>(ns_end - ns_begin);
+        prm.dbg_clk[blockIdx.x * 16 + 7] = static_cast<long long>(ns_begin);
+        prm.dbg_clk[blockIdx.x * 16 + 8] = static_cast<long long>(ns_end);
     }
 }
 
@@ -168,16 +224,17 @@ __device__ __forceinline__ void idx_stage_target(const IdxPipe& pp, const Affini
     }
     tmem_st_wait();
     tc_fence_before_sync();
-    mbar_arrive_s(pp.q_full);
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive_s(pp.q_full);    // one arrival per epilogue warp
 }
 
-template <int kStages>
+template <int kGroup, int kStages>
 __device__ __forceinline__ IdxPipe idx_setup(uint8_t* smem_raw, const CUtensorMap* tmap_hi, const CUtensorMap* tmap_lo,
-                                             int n_acc_bufs, int epi_threads) {
+                                             int n_acc_bufs, int epi_warps) {
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     IdxPipe pp;
     pp.r_smem = base;
-    pp.full = base + kStages * kChunkBytes;
+    pp.full = base + kStages * kGroup * kChunkBytes;
     pp.empty = pp.full + 8 * kStages;
     pp.q_full = pp.empty + 8 * kStages;
     pp.q_empty = pp.q_full + 8;
@@ -189,9 +246,9 @@ __device__ __forceinline__ IdxPipe idx_setup(uint8_t* smem_raw, const CUtensorMa
         prefetch_tmap(tmap_hi);
         prefetch_tmap(tmap_lo);
         for (int i = 0; i < kStages; ++i) { mbar_init_s(pp.full + 8 * i, 1); mbar_init_s(pp.empty + 8 * i, 1); }
-        mbar_init_s(pp.q_full, epi_threads);
+        mbar_init_s(pp.q_full, epi_warps);
         mbar_init_s(pp.q_empty, 1);
-        for (int i = 0; i < n_acc_bufs; ++i) { mbar_init_s(pp.acc_full + 8 * i, 1); mbar_init_s(pp.acc_empty + 8 * i, epi_threads); }
+        for (int i = 0; i < n_acc_bufs; ++i) { mbar_init_s(pp.acc_full + 8 * i, 1); mbar_init_s(pp.acc_empty + 8 * i, epi_warps); }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -381,21 +438,121 @@ __device__ __forceinline__ void gather_mixed(RowAcc<D>& st, const float (&v)[kQC
     add_to_class<D>(st, static_cast<int>(c), fmaxf(rest, 0.f) * scale);
 }
 
+// Chain initialisation of one 16-column step (see step16_chain): G, Rho and the factor 2^sh still missing from the sums.
+__device__ __forceinline__ void chain_init(float a0, float b0, float gamma, float2& G, float2& Rho, float& scale) {
+    const float sh = fmaxf(a0, fmaf(15.f, b0, fmaf(225.f, gamma, a0)));
+    const float a1 = a0 - sh;
+    const float r0 = fmaf(4.f, gamma, 2.f * b0);
+    G = make_float2(ex2(a1), ex2(a1 + b0 + gamma));
+    Rho = make_float2(ex2(r0), ex2(fmaf(4.f, gamma, r0)));
+    scale = ex2(sh);
+}
+
+// ---- Fast tile path: this warp's 32 columns are all real and the recurrence is safe for the whole frame
+// (PriorConst::chain_always).  Per-step bookkeeping (validity masks, path selection) is decided once per tile by the
+// caller; the common case (no image-row wrap inside the 32 columns) is straight-line code with two independent
+// 16-column chains.  The first capture of the single-pass kernel showed every epilogue warp latency-bound on that
+// bookkeeping (~9 cycles per instruction, 4 warps per scheduler), not on MUFU or issue slots.
+// jw = first of the 32 columns that lies on the next image row (>= 32: none).
+template <int D>
+__device__ __forceinline__ void fast_tile32(RowAcc<D>& st, float (&va)[kQC], float (&vb)[kQC], uint32_t cls_lane, uint32_t cls0,
+                                            uint32_t same32, int dn, float bx, int jw, const PriorConst& pc, float inv_w,
+                                            float scale2, float w_lowres) {
+    const uint32_t full = 0xffffffffu;
+    {
+        const float m_new = fmaxf(st.m, fmaxf(max16(va), max16(vb)) * scale2);
+        if (m_new > st.m) {
+            const float corr = ex2(st.m - m_new);
+            st.l *= corr;
+#pragma unroll
+            for (int c = 0; c < D; ++c) st.acc[c] *= corr;
+            st.m = m_new;
+        }
+    }
+    const float drc = static_cast<float>(dn) * inv_w;
+    float ta, tb, sa, sb;           // step sums (of v[]) and the factors still missing from them
+    if (jw >= 2 * kQC) {
+        const float neg_m = -st.m;
+        const float2 s2 = make_float2(scale2, scale2);
+        const float2 nm2 = make_float2(neg_m, neg_m);
+        const float2 K8 = make_float2(pc.k8, pc.k8);
+        float a0, b0;
+        quad_coeffs(drc, bx, inv_w, pc.coef, 0.f, a0, b0);
+        const float a1 = fmaf(16.f, b0, fmaf(256.f, pc.gamma, a0)), b1 = fmaf(32.f, pc.gamma, b0);   // the same parabola at column 16
+        float2 Ga, Ra, Gb, Rb;
+        chain_init(a0, b0, pc.gamma, Ga, Ra, sa);
+        chain_init(a1, b1, pc.gamma, Gb, Rb, sb);
+        float2 l2 = make_float2(0.f, 0.f), suma = make_float2(0.f, 0.f), sumb = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < kQC; j += 2) {
+            const float2 ea = ffma2(make_float2(va[j], va[j + 1]), s2, nm2);
+            const float2 eb = ffma2(make_float2(vb[j], vb[j + 1]), s2, nm2);
+            const float2 pa = make_float2(ex2(ea.x), ex2(ea.y));
+            const float2 pb = make_float2(ex2(eb.x), ex2(eb.y));
+            l2 = fadd2(l2, fadd2(pa, pb));
+            const float2 wa = fmul2(pa, Ga), wb = fmul2(pb, Gb);
+            suma = fadd2(suma, wa);
+            sumb = fadd2(sumb, wb);
+            va[j] = wa.x; va[j + 1] = wa.y;
+            vb[j] = wb.x; vb[j + 1] = wb.y;
+            if (j + 2 < kQC) {
+                Ga = fmul2(Ga, Ra); Ra = fmul2(Ra, K8);
+                Gb = fmul2(Gb, Rb); Rb = fmul2(Rb, K8);
+            }
+        }
+        st.l += l2.x + l2.y;
+        ta = suma.x + suma.y;
+        tb = sumb.x + sumb.y;
+    } else {
+        // one image-row wrap inside the 32 columns: the half that contains it evaluates its exponents directly,
+        // the other half runs its chain with the geometry of its own row
+        float a0, b0;
+        if (jw < kQC) {
+            sa = step16_direct<D>(st, va, drc, bx, jw, 0xffffu, pc, inv_w, scale2, w_lowres, ta);
+        } else {
+            quad_coeffs(drc, bx, inv_w, pc.coef, 0.f, a0, b0);
+            sa = step16_chain<D>(st, va, a0, b0, fmaxf(a0, fmaf(15.f, b0, fmaf(225.f, pc.gamma, a0))), true, pc, scale2, ta);
+        }
+        const float drc_b = static_cast<float>(dn + kQC) * inv_w;
+        if (jw > kQC) {
+            sb = step16_direct<D>(st, vb, drc_b, bx + static_cast<float>(kQC), jw - kQC, 0xffffu, pc, inv_w, scale2, w_lowres, tb);
+        } else {
+            quad_coeffs(drc_b, bx + static_cast<float>(kQC) - w_lowres, inv_w, pc.coef, 0.f, a0, b0);
+            sb = step16_chain<D>(st, vb, a0, b0, fmaxf(a0, fmaf(15.f, b0, fmaf(225.f, pc.gamma, a0))), true, pc, scale2, tb);
+        }
+    }
+    if (same32 == full) {                                   // one class in all 32 columns (the common case)
+        add_to_class<D>(st, static_cast<int>(cls0), fmaf(ta, sa, tb * sb));
+        return;
+    }
+    {
+        const uint32_t mk = same32 & 0xffffu;
+        if (mk == 0xffffu) add_to_class<D>(st, static_cast<int>(cls0), ta * sa);
+        else gather_mixed<D>(st, va, cls_lane, 0, 0xffffu, cls0, mk, ta, sa);
+    }
+    {
+        const uint32_t c = __shfl_sync(full, cls_lane, kQC);
+        const uint32_t mk = __ballot_sync(full, cls_lane == c) >> kQC;
+        if (mk == 0xffffu) add_to_class<D>(st, static_cast<int>(c), tb * sb);
+        else gather_mixed<D>(st, vb, cls_lane, kQC, 0xffffu, c, mk, tb, sb);
+    }
+}
+
 template <int D, bool kSplit>
-__global__ void __launch_bounds__(kIdxThreads, 1)
+__global__ void __launch_bounds__(kIdxThreads, 1)   // 18 warps: 5 on two of the schedulers -> 16384 / (5 * 32) = 96 registers
 vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
                  const __grid_constant__ AffinityParams prm) {
     using Cfg = IdxCfg<kSplit>;
     extern __shared__ uint8_t smem_raw[];
-    const IdxPipe pp = idx_setup<kIdxStages>(smem_raw, &tmap_hi, &tmap_lo, Cfg::kAccBufs, kIdxEpiThreads);
+    const IdxPipe pp = idx_setup<Cfg::kGroup, Cfg::kStages>(smem_raw, &tmap_hi, &tmap_lo, Cfg::kAccBufs, kIdxEpiWarps);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const vosd::Decomp dec = vosd::make_decomp(prm.n_pixels, prm.n_refs, prm.num_sms);
 
     if (warp == 0) {
-        idx_role_producer<kSplit, kIdxStages>(pp, &tmap_hi, &tmap_lo, prm, dec);
+        idx_role_producer<kSplit, Cfg::kGroup, Cfg::kStages>(pp, &tmap_hi, &tmap_lo, prm, dec);
     } else if (warp == 1) {
-        idx_role_mma<kSplit, kIdxStages>(pp, prm, dec);
+        idx_role_mma<kSplit, Cfg::kGroup, Cfg::kStages>(pp, prm, dec);
     } else {
         // ================= epilogue: warps 2-17; TMEM lanes [32*(warp%4), +32); logit columns [32*sub, +32)
         const uint32_t full = 0xffffffffu;
@@ -426,24 +583,47 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             int dn = j * kTile + sub * 32 - m;            // pixel-index difference of that column to the target pixel
             const uint8_t* cls_p = prm.cls + static_cast<size_t>(prm.ref_slot[r]) * prm.p_pad + j * kTile + sub * 32 + lane;
             PriorConst pc = prior_const(prm.ref_coef[r], inv_w, w_f, h_f);
+            uint32_t cls_next = __ldg(cls_p);                        // class byte of logit column `lane`, one tile ahead
             for (int nt = n0; nt < n1; ++nt) {
-                const uint32_t cls_lane = __ldg(cls_p);              // class byte of logit column `lane`
+                const uint32_t cls_lane = cls_next;
+                {   // prefetch the next tile's class bytes: the load's latency hides behind this tile's arithmetic
+                    const bool wrap_ref = j + 1 == dec.tpf;
+                    const uint8_t* nxt = wrap_ref ? prm.cls + static_cast<size_t>(prm.ref_slot[min(r + 1, prm.n_refs - 1)]) * prm.p_pad + sub * 32 + lane
+                                                  : cls_p + kTile;
+                    if (nt + 1 < n1) cls_next = __ldg(nxt);
+                }
                 const uint32_t valid32 = (j == dec.tpf - 1) ? ragged : full;
                 mbar_wait_s(pp.acc_full + 8 * buf, aphase);
                 tc_fence_after_sync();
                 const uint32_t taddr = pp.tmem_base + lane_base + buf * kTile + sub * 32;
                 const uint32_t cls0 = __shfl_sync(full, cls_lane, 0);
                 const uint32_t same32 = __ballot_sync(full, cls_lane == cls0);
+                if (valid32 == full && pc.chain_always && prm.dbg == 0) {
+                    float va[kQC], vb[kQC];
+                    tmem_ld_32x32b_x16(taddr, va);
+                    tmem_ld_32x32b_x16(taddr + kQC, vb);
+                    tmem_ld_wait();
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_s(pp.acc_empty + 8 * buf);
+                    fast_tile32<D>(st, va, vb, cls_lane, cls0, same32, dn, static_cast<float>(x_sub - xm), W - x_sub, pc, inv_w, scale2, w_f);
+                } else {
                 int xq = x_sub;
 #pragma unroll 1
                 for (int q = 0; q < 2; ++q) {
                     float v[kQC];
-                    tmem_ld_32x32b_x16(taddr + q * kQC, v);
-                    tmem_ld_wait();
+                    if (prm.dbg & 32) {
+#pragma unroll
+                        for (int i = 0; i < kQC; ++i) v[i] = 0.f;
+                    } else {
+                        tmem_ld_32x32b_x16(taddr + q * kQC, v);
+                        tmem_ld_wait();
+                    }
                     if (q == 1) {                                    // both halves of this warp's columns are in registers
                         tc_fence_before_sync();
-                        mbar_arrive_s(pp.acc_empty + 8 * buf);
-                    }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_s(pp.acc_empty + 8 * buf);   // one arrival per warp: 512 per-thread
+                    }                                                            // arrivals serialise on the barrier word
                     const int lane_shift = q * kQC;
                     const uint32_t valid = (valid32 >> lane_shift) & 0xffffu;
                     const int jw = W - xq;                            // first column of the step on the next image row
@@ -452,12 +632,13 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                     xq += kQC;
                     if (xq >= W) xq -= W;
                     if (valid == 0u) continue;                       // beyond the frame's last pixel
+                    if (prm.dbg & 1) { st.l += v[0]; continue; }
                     if (valid != 0xffffu) {
 #pragma unroll
                         for (int i = 0; i < kQC; ++i)
                             if (!((valid >> i) & 1u)) v[i] = -INFINITY;
                     }
-                    update_max<D>(st, v, scale2);
+                    if (!(prm.dbg & 8)) update_max<D>(st, v, scale2);
                     float sum, scale;
                     bool fast = jw >= kQC && valid == 0xffffu;
                     float a0, b0, sh;
@@ -475,9 +656,17 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                             fast = __all_sync(full, !live || chain_ok);
                         }
                     }
+                    if (prm.dbg & 4) { a0 = 0.f; b0 = 0.f; sh = 0.f; live = true; fast = true; }
+                    if (prm.dbg & 16) {
+                        float l = 0.f;
+#pragma unroll
+                        for (int i = 0; i < kQC; ++i) l += ex2(fmaf(v[i], scale2, -st.m));
+                        st.l += l; sum = l; scale = 1.f;
+                    } else
                     if (fast) scale = step16_chain<D>(st, v, a0, b0, sh, live, pc, scale2, sum);
                     else scale = step16_direct<D>(st, v, drc, bx, jw, valid, pc, inv_w, scale2, w_f, sum);
                     // ---- label gather: add each column's weight to its class (class bytes are warp-uniform per column)
+                    if (prm.dbg & 2) { st.acc[0] += sum * scale; continue; }
                     uint32_t c = cls0, mk = same32 & 0xffffu;
                     if (q == 1 || valid != 0xffffu) {
                         c = __shfl_sync(full, cls_lane, lane_shift + __ffs(valid) - 1);
@@ -485,6 +674,7 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                     }
                     if (mk == valid) add_to_class<D>(st, static_cast<int>(c), sum * scale);   // one class (common)
                     else gather_mixed<D>(st, v, cls_lane, lane_shift, valid, c, mk, sum, scale);
+                }
                 }
                 if (++buf == Cfg::kAccBufs) { buf = 0; aphase ^= 1; }
                 // next tile: 128 pixels further in the same frame, or tile 0 of the next reference frame

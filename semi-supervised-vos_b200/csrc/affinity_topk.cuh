@@ -19,12 +19,13 @@
 
 namespace vosk {
 
-constexpr int kTopkStages = 6;                 // 6 x 16 KiB reference chunks in flight
+constexpr int kTopkGroup = 2;                  // chunks per pipeline stage
+constexpr int kTopkStages = 3;                 // 3 x 32 KiB of reference chunks in flight
 constexpr int kTopkBuf = 112;                  // candidate slots per target pixel
 constexpr int kTopkMax = 64;                   // largest supported k  (kTopkBuf - 16 - kTopkMax >= 32 free slots after a prune)
 constexpr int kTopkEpiThreads = 128;
 constexpr int kTopkThreads = 64 + kTopkEpiThreads;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
-constexpr int kTopkSmem = kTopkStages * kChunkBytes + 512 + 1024 + kTopkBuf * kTile * 8;
+constexpr int kTopkSmem = kTopkStages * kTopkGroup * kChunkBytes + 512 + 1024 + kTopkBuf * kTile * 8;
 constexpr int kTopkMaxLists = 32;              // per-segment lists merged per target pixel (finish kernel)
 
 // order-preserving map float -> uint32 (larger float <=> larger key); -0.0 must be normalised to +0.0 by the caller
@@ -103,15 +104,15 @@ vos_affinity_topk(const __grid_constant__ CUtensorMap tmap_hi, const __grid_cons
                   const __grid_constant__ AffinityParams prm) {
     using Cfg = IdxCfg<kSplit>;
     extern __shared__ uint8_t smem_raw[];
-    const IdxPipe pp = idx_setup<kTopkStages>(smem_raw, &tmap_hi, &tmap_lo, Cfg::kAccBufs, kTopkEpiThreads);
+    const IdxPipe pp = idx_setup<kTopkGroup, kTopkStages>(smem_raw, &tmap_hi, &tmap_lo, Cfg::kAccBufs, kTopkEpiThreads / 32);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const vosd::Decomp dec = vosd::make_decomp(prm.n_pixels, prm.n_refs, prm.num_sms);
 
     if (warp == 0) {
-        idx_role_producer<kSplit, kTopkStages>(pp, &tmap_hi, &tmap_lo, prm, dec);
+        idx_role_producer<kSplit, kTopkGroup, kTopkStages>(pp, &tmap_hi, &tmap_lo, prm, dec);
     } else if (warp == 1) {
-        idx_role_mma<kSplit, kTopkStages>(pp, prm, dec);
+        idx_role_mma<kSplit, kTopkGroup, kTopkStages>(pp, prm, dec);
     } else {
         // ================= epilogue: warps 2-5; warp w owns TMEM lanes [32*(w%4), +32) = 32 target pixels
         const uint32_t full = 0xffffffffu;
@@ -146,7 +147,8 @@ vos_affinity_topk(const __grid_constant__ CUtensorMap tmap_hi, const __grid_cons
                     tmem_ld_wait();
                     if (s == kTile / kQC - 1) {                               // the whole tile row is in registers / consumed
                         tc_fence_before_sync();
-                        mbar_arrive_s(pp.acc_empty + 8 * buf);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_s(pp.acc_empty + 8 * buf);  // one arrival per warp
                     }
                     const int nv = cols - s * kQC;
                     if (nv <= 0) continue;

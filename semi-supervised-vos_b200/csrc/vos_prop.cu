@@ -54,6 +54,8 @@ struct vosprop_engine {
     // geometry of the current video
     int H_d = 0, W_d = 0, H = 0, W = 0, d = 0, P = 0, p_pad = 0;
     int precision = VOSPROP_PREC_SPLIT3;
+    int dbg = 0;
+    long long* dbg_clk = nullptr;
     __nv_bfloat16* ring_hi = nullptr;
     __nv_bfloat16* ring_lo = nullptr;
     float* meta = nullptr;
@@ -441,6 +443,8 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     ap.meta = e->meta; ap.partials = e->partials; ap.ring_hi = e->ring_hi; ap.ring_lo = e->ring_lo;
     ap.cls = e->cls; ap.inv_w = 1.0f / static_cast<float>(e->W_d);
     ap.feat_fmt = e->precision;
+    ap.dbg = e->dbg;
+    ap.dbg_clk = e->dbg_clk;
     ap.idesc = vosptx::umma_idesc_f32acc(vosk::kTile, vosk::kTile, e->precision == VOSPROP_PREC_F16 ? 0u : 1u);
     // the index-label kernel needs one class byte per reference pixel and W_d >= 32; anything else
     // (dense / probability labels, tiny maps) runs on the general tensor-core kernel
@@ -524,6 +528,18 @@ int vosprop_plan_step(int32_t frame_idx, int32_t take_range, int32_t num_refs, f
         step->ref_sigma[r] = probability_propagation ? 0.f : sg;
     }
     step->probability_propagation = probability_propagation;
+    return VOSPROP_OK;
+}
+
+int vosprop_debug_flags(vosprop_engine* e, int32_t flags) {
+    if (!e) return fail(VOSPROP_ERR_INVALID, "null engine");
+    e->dbg = flags;
+    return VOSPROP_OK;
+}
+
+int vosprop_debug_clocks(vosprop_engine* e, void* device_buffer) {
+    if (!e) return fail(VOSPROP_ERR_INVALID, "null engine");
+    e->dbg_clk = static_cast<long long*>(device_buffer);
     return VOSPROP_OK;
 }
 

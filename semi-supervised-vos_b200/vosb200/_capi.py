@@ -54,6 +54,8 @@ EXPORTS = {
     'vosprop_num_sms': (C.c_int, [C.c_void_p]),
     'vosprop_debug_decompose': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
                                            C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    'vosprop_debug_flags': (C.c_int, [C.c_void_p, C.c_int32]),
+    'vosprop_debug_clocks': (C.c_int, [C.c_void_p, C.c_void_p]),
     'vosprop_launch_count': (C.c_int64, [C.c_void_p]),
     'vosprop_timing_enable': (C.c_int, [C.c_void_p, C.c_int32]),
     'vosprop_timing_read': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

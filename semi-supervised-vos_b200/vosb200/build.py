@@ -9,7 +9,7 @@ from pathlib import Path
 CSRC = Path(__file__).resolve().parent.parent / 'csrc'
 LIB = CSRC / 'libvosprop.so'
 SOURCES = ['vos_prop.cu']
-HEADERS = ['kernels.cuh', 'ptx.cuh', 'decompose.h', '../../include/vos_prop.h']
+HEADERS = ['kernels.cuh', 'affinity_idx.cuh', 'affinity_topk.cuh', 'ptx.cuh', 'decompose.h', '../../include/vos_prop.h']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared', '-cudart', 'static']
 
