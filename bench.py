@@ -44,7 +44,7 @@ REF_NUM, FRAME_RANGE, SIGMA_1, SIGMA_2, TEMPERATURE = 9, 40, 8.0, 21.0, 1.0
 METRIC = 'propagated frames/sec at 480p'
 # dram__bytes_read.sum + dram__bytes_write.sum of one vos_affinity_idx launch (R = 9) from the ncu --set full
 # captures under profiles/ (see profiles/README.md); None until captured for that mode
-TRAFFIC_BYTES = {'f16': None, 'split3': 63.4e6}
+TRAFFIC_BYTES = {'f16': 33.7e6, 'split3': 63.4e6}
 UNIT = 'frames/s'
 
 

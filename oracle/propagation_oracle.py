@@ -145,7 +145,8 @@ def predict(ref: torch.Tensor, target: torch.Tensor, ref_label: torch.Tensor,
             take_range: int, ref_num: int, temperature: float,
             probability_propagation: bool, chunk: Optional[int] = None,
             topk: Optional[int] = None, return_topk_idx: bool = False,
-            weights: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+            weights: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+            pixel_range: Optional[Tuple[int, int]] = None):
     """Label propagation for one target frame.
 
     ref (T,K,H,W) fp32, target (K,H,W), ref_label (d,T,P) -> prediction (d,P) fp32.
@@ -156,6 +157,9 @@ def predict(ref: torch.Tensor, target: torch.Tensor, ref_label: torch.Tensor,
     reference passes them (built once per video by prepare_first_frame, predict.py:117-118).
     ``chunk``: process target pixels in column blocks of this size (softmax over dim 0 is
     per-column, so chunking is exact up to GEMM blocking).
+    ``pixel_range``: (p0, p1) -- evaluate only target pixels p0..p1-1 and return (d, p1-p0); every target
+    pixel is independent (softmax over dim 0), so this is the corresponding column block of the full result.
+    Used where the full product is too large for a CPU test (1080p: 291 600 x 32 400).
     ``topk``: EXTENSION (not in the reference): the softmax of predict.py:55 is
     restricted, per target pixel, to the k reference pixels with the largest logit (ties ->
     lowest reference index first); everything else gets weight 0.  The prior and label gather
@@ -173,8 +177,9 @@ def predict(ref: torch.Tensor, target: torch.Tensor, ref_label: torch.Tensor,
     topk_idx = torch.empty(P, topk, dtype=torch.long) if (topk and return_topk_idx) else None
     step = P if chunk is None else chunk
     use_prior = not probability_propagation
-    for c0 in range(0, P, step):
-        cs = slice(c0, min(c0 + step, P))
+    p0, p1 = (0, P) if pixel_range is None else pixel_range
+    for c0 in range(p0, p1, step):
+        cs = slice(c0, min(c0 + step, p1))
         S = ref_mat.mm(tgt[:, cs])                                       # :49
         S *= temperature                                                 # :52
         if topk is not None and topk < S.shape[0]:
@@ -199,6 +204,9 @@ def predict(ref: torch.Tensor, target: torch.Tensor, ref_label: torch.Tensor,
                 S = S.mul(w_dense)
             S = S.reshape(R * P, -1)
         out[:, cs] = lab_sel.mm(S.float())                               # :70
+    if pixel_range is not None:
+        out = out[:, p0:p1]
+        topk_idx = topk_idx[p0:p1] if topk_idx is not None else None
     if return_topk_idx:
         return out, topk_idx
     return out

@@ -1,0 +1,124 @@
+"""GPU parity on the shapes of BASELINE.json's other configurations (the bench line is config[1]):
+ref_num / frame_range sweeps (config 3), 1080p maps (config 4), up to 10 objects and clips of different geometry
+through one engine (config 5).  Oracle = CPU restatement of the reference (oracle/), same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import propagation_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+PROB_ATOL = 1e-3
+MASK_AGREE = 0.999
+
+
+def _engine(max_pixels, ring_slots=48):
+    from vosb200 import PropagationEngine
+    return PropagationEngine(max_pixels=max_pixels, ring_slots=ring_slots)
+
+
+@pytest.mark.parametrize('prec', ['f16', 'split3'])
+def test_ten_objects_index_kernel(prec):
+    """d = 11 classes on a map wide enough (W_d >= 32) for the index-label kernel; YouTube-VOS-shaped object count."""
+    from vosb200.sequence import propagate_clip
+    feats, first = O.synthetic_sequence(12, 160, 320, 10, seed=23, feat_scale=0.30)
+    if prec == 'f16':
+        feats = feats.half()
+    eng = _engine(feats.shape[2] * feats.shape[3])
+    masks, preds = propagate_clip(eng, feats.cuda(), first, return_predictions=True)
+    want_masks, want_preds = O.propagate_sequence(feats.float(), first)
+    agree = float((masks.cpu().long() == want_masks).float().mean())
+    err = float((preds.cpu() - torch.stack(want_preds)).abs().max())
+    print(f'10 objects/{prec}: d={preds.shape[1]}, mask agreement {agree:.6f}, max |dP| {err:.3e}')
+    assert preds.shape[1] == 11 and agree >= MASK_AGREE
+    if agree == 1.0:
+        assert err <= PROB_ATOL
+
+
+@pytest.mark.parametrize('ref_num,frame_range', [(3, 40), (4, 40), (5, 10), (12, 40), (20, 40), (9, 2)])
+def test_ref_num_and_range_sweep(ref_num, frame_range):
+    """Whole clips long enough to leave the ramp (frame_idx > ref_num), pass frame 15 (sigma switch) and wrap the
+    48-slot ring; (9, 2) makes sample_frames return duplicated references."""
+    from vosb200.sequence import propagate_clip
+    feats, first = O.synthetic_sequence(56, 136, 264, 2, seed=29, feat_scale=0.30)
+    feats = feats.half()
+    eng = _engine(feats.shape[2] * feats.shape[3])
+    masks, preds = propagate_clip(eng, feats.cuda(), first, ref_num=ref_num, frame_range=frame_range, return_predictions=True)
+    want_masks, want_preds = O.propagate_sequence(feats.float(), first, ref_num=ref_num, frame_range=frame_range)
+    agree = float((masks.cpu().long() == want_masks).float().mean())
+    err = float((preds.cpu() - torch.stack(want_preds)).abs().max())
+    print(f'ref_num={ref_num} range={frame_range}: mask agreement {agree:.6f}, max |dP| {err:.3e}')
+    assert agree >= MASK_AGREE
+    if agree == 1.0:
+        assert err <= PROB_ATOL
+
+
+def test_ref_num_below_three_raises_like_the_reference():
+    from vosb200 import plan_refs
+    with pytest.raises(ValueError):   # np.linspace with a negative count in the reference
+        plan_refs(5, 40, 2, 8.0, 21.0, False)
+    assert plan_refs(2, 40, 2, 8.0, 21.0, False)[0] == [0, 1]
+
+
+@pytest.mark.parametrize('topk', [0, 20])
+def test_1080p_pixel_blocks_against_oracle(topk):
+    """1080p: 135 x 240 = 32 400 pixels, 254 tiles (the last one 16 pixels wide), N = 291 600 at R = 9.  The full
+    product is too large for a CPU test, so the oracle evaluates blocks of target pixels (each target pixel is an
+    independent softmax): the first tile, a block across a tile boundary in the middle, and the ragged tail."""
+    from vosb200 import PREC_F16, plan_refs
+    T, t = 10, 9
+    feats, first = O.synthetic_sequence(T, 1080, 1920, 3, seed=37, feat_scale=0.30)
+    feats = feats.half().float()
+    _, K, H_d, W_d = feats.shape
+    P = H_d * W_d
+    assert (H_d, W_d) == (135, 240)
+    low, d = O.first_frame_labels(first)
+    g = torch.Generator().manual_seed(3)
+    cls = torch.randint(0, d, (T, P), generator=g)
+    cls[0] = low
+    cls[2::2] = torch.where(torch.rand(T, P, generator=g)[2::2] < 0.98, cls[2::2] * 0, cls[2::2])   # mostly homogeneous frames
+    hist = torch.stack([O.index_to_onehot(cls[f], d) for f in range(T)], 1)
+    eng = _engine(P, ring_slots=12)
+    eng.reset(H_d, W_d, 1080, 1920, d, PREC_F16)
+    gf = feats.cuda().half()
+    for f in range(T):
+        eng.append(f, gf[f])
+        eng.set_labels_index(f, cls[f].to(torch.uint8).cuda())
+    refs, sig = plan_refs(t, 40, 9, 8.0, 21.0, False)
+    out = eng.propagate(t, refs, sig, 1.0, False, write_labels=False, topk=topk, want_topk_idx=topk > 0)
+    got = out['prediction'].cpu()
+    for (p0, p1) in ((0, 160), (16200 - 96, 16200 + 96), (P - 144, P)):
+        res = O.predict(feats[:t], feats[t], hist[:, :t], 8.0, 21.0, t, 40, 9, 1.0, False, chunk=96,
+                        topk=topk or None, return_topk_idx=topk > 0, pixel_range=(p0, p1))
+        want = res[0] if topk else res
+        err = float((got[:, p0:p1] - want).abs().max())
+        agree = float((got[:, p0:p1].argmax(0) == want.argmax(0)).float().mean())
+        print(f'1080p topk={topk} pixels [{p0},{p1}): max |dP| {err:.3e}, argmax agreement {agree:.6f}')
+        if topk:
+            same_set = (out['topk_idx'].cpu().long()[p0:p1].sort(1).values == res[1].sort(1).values).all(1)
+            assert float(same_set.float().mean()) >= 0.98
+            assert float((got[:, p0:p1] - want).abs()[:, same_set].max()) <= PROB_ATOL
+        else:
+            assert err <= PROB_ATOL and agree >= 0.99
+    full = O.upsample_mask(out['mask_lowres'].cpu().long(), H_d, W_d, 1080, 1920)
+    assert torch.equal(out['mask'].cpu().long(), full)
+
+
+def test_clips_of_different_geometry_through_one_engine():
+    """YouTube-VOS-shaped use: one engine (one ring) serves clips of different size, length and object count one
+    after the other; nothing of a previous clip may leak (ring padding rows, class bytes, label records)."""
+    from vosb200.sequence import propagate_clip
+    eng = _engine(40 * 72)
+    for (T, H, W, n_obj, seed, dt) in ((9, 320, 576, 4, 61, torch.float16), (14, 136, 264, 1, 62, torch.float32),
+                                       (7, 264, 328, 7, 63, torch.float16), (9, 320, 576, 2, 64, torch.bfloat16)):
+        feats, first = O.synthetic_sequence(T, H, W, n_obj, seed=seed, feat_scale=0.30)
+        feats = feats.to(dt)
+        masks, preds = propagate_clip(eng, feats.cuda(), first, return_predictions=True)
+        want_masks, want_preds = O.propagate_sequence(feats.float(), first)
+        agree = float((masks.cpu().long() == want_masks).float().mean())
+        err = float((preds.cpu() - torch.stack(want_preds)).abs().max())
+        print(f'clip {H}x{W} T={T} objects={n_obj} {dt}: mask agreement {agree:.6f}, max |dP| {err:.3e}')
+        assert agree >= MASK_AGREE
+        if agree == 1.0:
+            assert err <= PROB_ATOL
