@@ -472,6 +472,9 @@ struct MergeParams {
     int32_t write_labels, probability;
     int32_t n_sub;             // partial records per (CTA, segment): 2 (half tiles) or 4 (quarter tiles)
     const float* partials;
+    const int32_t* tables;     // host-computed decomposition tables (no 64-bit divisions in the kernel):
+                               // [0, tpf) first CTA of each target tile, [tpf, 2 tpf) last CTA, [2 tpf, 2 tpf + grid) first target tile of each CTA
+    int32_t tpf, max_segs;
     float* meta;
     uint8_t* cls;              // class-id ring (index-label mode of the next steps)
     float* out_prediction;     // (d, P) or null
@@ -484,20 +487,31 @@ __device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
     return min(static_cast<int>(floorf(static_cast<float>(dst) * scale)), in_size - 1);
 }
 
+// Decomposition tables for vos_merge_writeback (layout: MergeParams::tables); 64-bit divisions happen here, once per
+// (video, reference count), instead of per pixel in the merge.
+__global__ void vos_decomp_tables(int32_t* __restrict__ tab, int n_pixels, int n_refs, int num_sms) {
+    const vosd::Decomp dec = vosd::make_decomp(n_pixels, n_refs, num_sms);
+    for (int mt = threadIdx.x; mt < dec.tpf; mt += blockDim.x) {
+        tab[mt] = vosd::cta_of(dec, static_cast<int64_t>(mt) * dec.nt);
+        tab[dec.tpf + mt] = vosd::cta_of(dec, static_cast<int64_t>(mt) * dec.nt + dec.nt - 1);
+    }
+    for (int c = threadIdx.x; c < dec.grid; c += blockDim.x)
+        tab[2 * dec.tpf + c] = static_cast<int32_t>(vosd::cta_begin(dec, c) / dec.nt);
+}
+
 constexpr int kMergeThreads = 1024;   // 128 pixel groups of 8 lanes
 constexpr int kMergeLanes = 8;        // lanes cooperating on one target pixel
 
 __global__ void __launch_bounds__(kMergeThreads) vos_merge_writeback(const MergeParams prm) {
     extern __shared__ uint8_t row_cls[];  // [w_lowres]
     const int y = blockIdx.x;
-    const vosd::Decomp dec = vosd::make_decomp(prm.n_pixels, prm.n_refs, prm.num_sms);
     const int sublane = threadIdx.x & (kMergeLanes - 1);
     const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~(kMergeLanes - 1));   // the 8 lanes of this pixel group
+    const int32_t* mt0 = prm.tables + 2 * prm.tpf;
     for (int x = threadIdx.x / kMergeLanes; x < prm.w_lowres; x += kMergeThreads / kMergeLanes) {
         const int pix = y * prm.w_lowres + x;
         const int mt = pix / kTile, row = pix % kTile;
-        const int64_t lin_lo = static_cast<int64_t>(mt) * dec.nt;
-        const int c_first = vosd::cta_of(dec, lin_lo), c_last = vosd::cta_of(dec, lin_lo + dec.nt - 1);
+        const int c_first = prm.tables[mt], c_last = prm.tables[prm.tpf + mt];
         const int n_rec = (c_last - c_first + 1) * prm.n_sub;
         // each lane folds records sublane, sublane+8, ... (online softmax merge), then an 8-lane butterfly
         float M = kNegBig, L = 0.f, acc[kMaxClasses];
@@ -505,8 +519,8 @@ __global__ void __launch_bounds__(kMergeThreads) vos_merge_writeback(const Merge
         for (int k = 0; k < kMaxClasses; ++k) acc[k] = 0.f;
         for (int i = sublane; i < n_rec; i += kMergeLanes) {
             const int c = c_first + i / prm.n_sub, h = i % prm.n_sub;
-            const int seg = mt - static_cast<int>(vosd::cta_begin(dec, c) / dec.nt);
-            const float* rec = prm.partials + (static_cast<size_t>(c * dec.max_segs + seg) * prm.n_sub + h) * kPartFloats;
+            const int seg = mt - mt0[c];
+            const float* rec = prm.partials + (static_cast<size_t>(c * prm.max_segs + seg) * prm.n_sub + h) * kPartFloats;
             const float m_r = rec[row];
             const float M_new = fmaxf(M, m_r);
             const float w_old = vosptx::ex2(M - M_new), w_new = vosptx::ex2(m_r - M_new);
@@ -558,10 +572,10 @@ __global__ void __launch_bounds__(kMergeThreads) vos_merge_writeback(const Merge
     const int guess = static_cast<int>(static_cast<float>(y) / sy);
     const int span = static_cast<int>(1.0f / sy) + 2;
     const int dy0 = max(0, guess - span), dy1 = min(prm.H, guess + 2 * span);
-    for (int i = threadIdx.x; i < (dy1 - dy0) * prm.W; i += kMergeThreads) {
-        const int dy = dy0 + i / prm.W, dx = i % prm.W;
-        if (nearest_src(dy, sy, prm.h_lowres) != y) continue;
-        prm.out_mask_fullres[static_cast<size_t>(dy) * prm.W + dx] = row_cls[nearest_src(dx, sx, prm.w_lowres)];
+    for (int dx = threadIdx.x; dx < prm.W; dx += kMergeThreads) {
+        const uint8_t c = row_cls[nearest_src(dx, sx, prm.w_lowres)];
+        for (int dy = dy0; dy < dy1; ++dy)
+            if (nearest_src(dy, sy, prm.h_lowres) == y) prm.out_mask_fullres[static_cast<size_t>(dy) * prm.W + dx] = c;
     }
 }
 

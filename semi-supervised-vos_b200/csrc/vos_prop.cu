@@ -67,6 +67,10 @@ struct vosprop_engine {
     int32_t* cand_idx = nullptr;
     int32_t* cand_cnt = nullptr;
     uint8_t* low_scratch = nullptr;   // stride-8 class map when the caller wants only the full-resolution mask
+    // decomposition tables of the merge kernel, one per reference count (cached until the next reset)
+    int32_t* tables = nullptr;        // device [VOSPROP_MAX_REFS + 1][table_stride]
+    size_t table_stride = 0;
+    std::vector<char> table_valid;
     CUtensorMap tmap_hi{}, tmap_lo{};
     EncodeTiledFn encode = nullptr;
     std::vector<int> slot_frame;
@@ -269,6 +273,10 @@ int vosprop_create(const vosprop_config* cfg, vosprop_engine** out) {
     cudaError_t a3 = cudaMalloc(&e->meta, rows * vosk::kMetaFloats * 4);
     cudaError_t a4 = cudaMalloc(&e->partials, e->partial_records * vosk::kPartFloats * 4);
     cudaError_t a5 = cudaMalloc(&e->cls, rows);
+    e->table_stride = static_cast<size_t>(2 * tiles_cap + e->num_sms + 8);
+    e->table_valid.assign(VOSPROP_MAX_REFS + 1, 0);
+    cudaError_t a6 = cudaMalloc(&e->tables, (VOSPROP_MAX_REFS + 1) * e->table_stride * sizeof(int32_t));
+    if (a6 != cudaSuccess) a1 = a6;
     if (a1 != cudaSuccess || a2 != cudaSuccess || a3 != cudaSuccess || a4 != cudaSuccess || a5 != cudaSuccess) {
         vosprop_destroy(e);
         return fail(VOSPROP_ERR_CUDA, "cudaMalloc of the reference-memory ring failed (%zu rows)", rows);
@@ -297,6 +305,7 @@ void vosprop_destroy(vosprop_engine* e) {
     cudaFree(e->cand_idx);
     cudaFree(e->cand_cnt);
     cudaFree(e->low_scratch);
+    cudaFree(e->tables);
     for (cudaEvent_t ev : e->ev) cudaEventDestroy(ev);
     delete e;
 }
@@ -319,6 +328,7 @@ int vosprop_reset(vosprop_engine* e, int32_t H_d, int32_t W_d, int32_t H, int32_
     if (rc) return rc;
     std::fill(e->slot_frame.begin(), e->slot_frame.end(), -1);
     std::fill(e->slot_labels.begin(), e->slot_labels.end(), 0);
+    std::fill(e->table_valid.begin(), e->table_valid.end(), 0);
     const size_t n = static_cast<size_t>(e->cfg.ring_slots) * e->p_pad;
     vosk::vos_init_meta<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(e->meta, e->cfg.ring_slots, e->p_pad, e->P, W_d);
     VOS_CUDA(cudaGetLastError());
@@ -466,6 +476,17 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     mp.num_sms = e->num_sms; mp.d = e->d; mp.H = e->H; mp.W = e->W; mp.q_slot = q_slot;
     mp.write_labels = s->write_labels; mp.probability = s->probability_propagation;
     mp.n_sub = (kernel == VOSPROP_KERNEL_TC) ? vosk::kIdxSub : 2;
+    {   // which CTAs hold partials of which target tile: computed once per reference count and video (tiny kernel,
+        // stream-ordered, so a host that runs clips ahead of the device never races with it)
+        int32_t* dev = e->tables + static_cast<size_t>(s->n_refs) * e->table_stride;
+        if (!e->table_valid[s->n_refs]) {
+            vosk::vos_decomp_tables<<<1, 256, 0, st>>>(dev, e->P, s->n_refs, e->num_sms);
+            VOS_CUDA(cudaGetLastError());
+            e->table_valid[s->n_refs] = 1;
+            e->launches++;
+        }
+        mp.tables = dev; mp.tpf = dec.tpf; mp.max_segs = dec.max_segs;
+    }
     mp.partials = e->partials; mp.meta = e->meta; mp.cls = e->cls;
     mp.out_prediction = s->out_prediction; mp.out_mask_lowres = s->out_mask_lowres; mp.out_mask_fullres = s->out_mask_fullres;
     {

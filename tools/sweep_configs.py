@@ -1,0 +1,75 @@
+"""Timing sweep over BASELINE.json's secondary configurations on one GPU (device time per propagated frame,
+CUDA events around the engine's kernels; steady state, frame_idx >= 44 so both sigma branches are active):
+
+  config 3: ref_num in {3, 5, 9, 12, 16, 20} x top-k in {full softmax, 5, 20, 50} at 480p
+  config 4: 1080p (135 x 240 features), ref_num 9
+  config 5: 10 objects (d = 11) at 480p
+
+Prints one JSON object per line; `python tools/sweep_configs.py > profiles/<name>.jsonl`."""
+import json
+import sys
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent.parent
+for p in (str(REPO), str(REPO / 'semi-supervised-vos_b200')):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+
+from vosb200 import PREC_F16, PREC_SPLIT3, PropagationEngine, plan_refs, synthetic  # noqa: E402
+from vosb200.sequence import lowres_dims  # noqa: E402
+
+K = 256
+
+
+def measure(H, W, n_obj, ref_num, topk, prec, frames=6, t0=46):
+    dev = torch.device('cuda', 0)
+    T = t0 + frames
+    H_d, W_d = lowres_dims(H, W)
+    P = H_d * W_d
+    g = torch.Generator(device=dev).manual_seed(1)
+    proto = torch.randn(n_obj + 1, K, device=dev, generator=g) * 0.3
+    eng = PropagationEngine(max_pixels=P, ring_slots=max(48, ref_num + 2), device=dev)
+    eng.reset(H_d, W_d, H, W, n_obj + 1, prec)
+    cm = synthetic._class_map(synthetic._tracks(n_obj, torch.Generator().manual_seed(2)), 0, H_d, W_d, dev).reshape(-1)
+    feat_dtype = torch.float16 if prec == PREC_F16 else torch.float32
+
+    def feature(t):
+        f = proto[cm] + 0.1 * torch.randn(P, K, device=dev, generator=g)
+        return f.t().reshape(K, H_d, W_d).to(feat_dtype).contiguous()
+
+    for t in range(t0 - 45, t0):                       # fill the ring's look-back window
+        eng.append(t, feature(t))
+        eng.set_labels_index(t, cm.to(torch.uint8))
+    feats = [feature(t) for t in range(t0, T)]
+    out = torch.empty((H, W), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    eng.enable_timing(8 * frames)
+    for i, t in enumerate(range(t0, T)):
+        eng.append(t, feats[i])
+        refs, sig = plan_refs(t, 40, ref_num, 8.0, 21.0, False)
+        eng.propagate(t, refs, sig, 1.0, False, want_prediction=False, want_lowres=False, want_fullres=False,
+                      out_fullres=out, topk=topk)
+    tm = eng.read_timing()
+    eng.close()
+    us = {k: v[0] / max(v[1], 1) * 1e3 for k, v in tm.items()}
+    total = sum(us.values())
+    flops = 2.0 * P * (len(refs) * P) * K
+    return {'H': H, 'W': W, 'pixels': P, 'objects': n_obj, 'ref_num': ref_num, 'refs_used': len(refs), 'topk': topk,
+            'precision': 'f16' if prec == PREC_F16 else 'split3', 'append_us': round(us['append'], 1),
+            'affinity_us': round(us['affinity'], 1), 'merge_us': round(us['merge'], 1),
+            'frames_per_s_device': round(1e6 / total, 1), 'affinity_tflops_algorithmic': round(flops / us['affinity'] / 1e6, 1)}
+
+
+def main():
+    for ref_num in (3, 5, 9, 12, 16, 20):
+        for topk in (0, 5, 20, 50):
+            print(json.dumps(dict(config=3, **measure(480, 854, 2, ref_num, topk, PREC_F16))), flush=True)
+    print(json.dumps(dict(config=3, **measure(480, 854, 2, 9, 0, PREC_SPLIT3))), flush=True)
+    for topk in (0, 20):
+        print(json.dumps(dict(config=4, **measure(1080, 1920, 3, 9, topk, PREC_F16, frames=3))), flush=True)
+    print(json.dumps(dict(config=4, **measure(1080, 1920, 3, 9, 0, PREC_SPLIT3, frames=3))), flush=True)
+    print(json.dumps(dict(config=5, **measure(480, 854, 10, 9, 0, PREC_F16))), flush=True)
+
+
+if __name__ == '__main__':
+    main()
