@@ -111,8 +111,8 @@ def nearest_src_index(out_size: int, in_size: int) -> np.ndarray:
     return np.minimum(src, in_size - 1)
 
 
-def first_frame_labels(label_full: np.ndarray, d: Optional[int] = None
-                       ) -> Tuple[torch.Tensor, int]:
+def first_frame_labels(label_full: np.ndarray, d: Optional[int] = None,
+                       dims: Optional[Tuple[int, int]] = None) -> Tuple[torch.Tensor, int]:
     """Full-res class-index annotation (H,W) -> low-res class index (P,) and d.
 
     src/model/predict.py:107-114 + get_labels :92-96 (one-hot at full res, nearest down-sample
@@ -122,7 +122,7 @@ def first_frame_labels(label_full: np.ndarray, d: Optional[int] = None
     H, W = label_full.shape
     if d is None:
         d = int(label_full.max()) + 1  # predict.py:113
-    H_d, W_d = lowres_dims(H, W)
+    H_d, W_d = lowres_dims(H, W) if dims is None else dims      # dims: second scale of the 2-scale strategies (predict.py:137-141)
     ys = nearest_src_index(H_d, H)
     xs = nearest_src_index(W_d, W)
     low = torch.from_numpy(np.ascontiguousarray(label_full[np.ix_(ys, xs)]).astype(np.int64))
@@ -257,6 +257,68 @@ def propagate_sequence(features: torch.Tensor, first_label_full: np.ndarray,
         masks.append(torch.argmax(up, 1)[0])                             # :75
         preds.append(pred)
     return torch.stack(masks), preds
+
+
+# --------------------------------------------------------------------------------------
+# Test-time-augmentation strategies: two independent memories + per-frame fusion
+# (src/utils/inference_utils.py:90-511)
+# --------------------------------------------------------------------------------------
+def _propagate_stream(features, low, d, out_hw, sigma_1, sigma_2, frame_range, ref_num, temperature,
+                      probability_propagation):
+    """One memory of a two-stream strategy: per frame the prediction nearest-up-sampled to out_hw, (1,d,H,W)."""
+    T, K, H_d, W_d = features.shape
+    label_history = index_to_onehot(low, d).unsqueeze(1)
+    feats_history = features[:1]
+    ups = []
+    for t in range(1, T):
+        pred = predict(feats_history, features[t], label_history, sigma_1, sigma_2, t, frame_range, ref_num,
+                       temperature, probability_propagation)
+        new_label = pred.unsqueeze(1) if probability_propagation else index_to_onehot(torch.argmax(pred, 0), d).unsqueeze(1)
+        label_history = torch.cat((label_history, new_label), 1)
+        feats_history = torch.cat((feats_history, features[t:t + 1]), 0)
+        ups.append(torch.nn.functional.interpolate(pred.view(1, d, H_d, W_d), size=out_hw, mode='nearest'))
+    return ups
+
+
+def propagate_two_streams(strategy: str, feats_a: torch.Tensor, feats_b: torch.Tensor, first_label_full: np.ndarray,
+                          sigma_1: float = 8.0, sigma_2: float = 21.0, frame_range: int = 40, ref_num: int = 9,
+                          temperature: float = 1.0, probability_propagation: bool = False, reduction: str = 'mean',
+                          scale: float = 1.15) -> torch.Tensor:
+    """inference_hor_flip (:90-192), inference_ver_flip (:195-298), inference_2_scale (:302-410, incl. 'hor-2-scale'),
+    inference_multimodel (:411-511) with the feature extractor factored out -> fused masks (T-1,H,W) uint8.
+    Quirks kept: both flip strategies un-flip stream B with torch.fliplr (:173, :279), which on the (1,d,H,W)
+    probability map flips the class axis; 'hor-2-scale' feeds stream B unflipped labels (predict.py:136-141);
+    probabilities are cast to half before the arg-max (:181)."""
+    H, W = first_label_full.shape
+    lab = np.asarray(first_label_full)
+    low_a, d = first_frame_labels(lab)
+    if strategy == 'hor-flip':
+        low_b, _ = first_frame_labels(np.ascontiguousarray(lab[:, ::-1]), d)
+    elif strategy == 'vert-flip':
+        low_b, _ = first_frame_labels(np.ascontiguousarray(lab[::-1]), d)
+    elif strategy in ('2-scale', 'hor-2-scale'):
+        low_b, _ = first_frame_labels(lab, d, dims=(int(np.ceil(H * SCALE * scale)), int(np.ceil(W * SCALE * scale))))
+    elif strategy == 'multimodel':
+        low_b = low_a
+    else:
+        raise ValueError(strategy)
+    args = (sigma_1, sigma_2, frame_range, ref_num, temperature, probability_propagation)
+    ups_a = _propagate_stream(feats_a, low_a, d, (H, W), *args)
+    ups_b = _propagate_stream(feats_b, low_b, d, (H, W), *args)
+    reduce = {'maximum': torch.maximum, 'minimum': torch.minimum, 'mean': lambda x, y: (x + y) / 2.0}[reduction]
+    out = []
+    for pa, pb in zip(ups_a, ups_b):
+        if not probability_propagation:
+            pa, pb = torch.argmax(pa, 1)[0], torch.argmax(pb, 1)[0]          # (H,W)
+        if strategy in ('hor-flip', 'vert-flip'):
+            pb = torch.fliplr(pb)
+        elif strategy == 'hor-2-scale':
+            pb = torch.flip(pb, dims=(-1,))
+        if probability_propagation:
+            out.append(torch.argmax(reduce(pa, pb).half(), 1)[0])
+        else:
+            out.append(torch.maximum(pa, pb))
+    return torch.stack(out).to(torch.uint8)
 
 
 # --------------------------------------------------------------------------------------

@@ -112,6 +112,59 @@ def run_inference_single(ref, features, first_label_full, palette, workdir, vide
     return masks.astype(np.uint8), recorded
 
 
+def run_inference_two_streams(ref, strategy, feats_a, feats_b, first_label_full, palette, workdir, size_b=None,
+                              video='clip', sigma_1=8.0, sigma_2=21.0, frame_range=40, ref_num=9, temperature=1.0,
+                              probability_propagation=False, reduction='mean', scale=1.15):
+    """Drive the reference's REAL test-time-augmentation loops (src/utils/inference_utils.py:90-511:
+    inference_hor_flip / inference_ver_flip / inference_2_scale / inference_multimodel) with table-lookup models.
+    feats_a / feats_b: (T,K,h,w) embeddings of the two streams; size_b: (H,W) of the second input when it differs
+    (2-scale).  Returns the fused masks (T-1,H,W) uint8 read back from the PNGs it wrote."""
+    import numpy as np
+    import torch
+    from PIL import Image
+
+    T = feats_a.shape[0]
+    H, W = first_label_full.shape
+    workdir = Path(workdir)
+    ann_dir = workdir / 'Annotations' / '480p'
+    (ann_dir / video).mkdir(parents=True, exist_ok=True)
+    img = Image.fromarray(first_label_full.astype(np.uint8), mode='P')
+    img.putpalette(palette)
+    img.save(ann_dir / video / '00000.png')
+    save = workdir / 'out'
+    Hb, Wb = (H, W) if size_b is None else size_b
+
+    def table(feats):
+        return lambda inp: feats[int(inp[0, 0, 0, 0].item())][None]
+
+    iu = ref.inference_utils
+    common = (T, ann_dir, video, str(save), sigma_1, sigma_2, frame_range, ref_num, temperature, probability_propagation)
+    with torch.no_grad():
+        if strategy == 'multimodel':
+            loader = [(torch.full((1, 1, H, W), float(t)), (video,)) for t in range(T)]
+            iu.inference_multimodel(table(feats_a), table(feats_b), loader, *common, reduction, True)
+        else:
+            loader = [([torch.full((1, 1, H, W), float(t)), torch.full((1, 1, Hb, Wb), float(t))], (video,)) for t in range(T)]
+            model = lambda inp: (feats_a if tuple(inp.shape[2:]) == (H, W) and not getattr(model, 'second', False) else feats_b)[int(inp[0, 0, 0, 0].item())][None]  # noqa: E731
+            if (Hb, Wb) == (H, W):
+                # same-sized inputs: the loops call model(input_l) then model(input_r) -- alternate
+                state = {'n': 0}
+
+                def model(inp):  # noqa: F811
+                    state['n'] += 1
+                    return (feats_a if state['n'] % 2 == 1 else feats_b)[int(inp[0, 0, 0, 0].item())][None]
+            if strategy == 'hor-flip':
+                iu.inference_hor_flip(model, loader, *common, reduction, True)
+            elif strategy == 'vert-flip':
+                iu.inference_ver_flip(model, loader, *common, reduction, True)
+            elif strategy in ('2-scale', 'hor-2-scale'):
+                iu.inference_2_scale(model, loader, *common, scale, reduction, strategy == 'hor-2-scale', True)
+            else:
+                raise ValueError(strategy)
+    masks = np.stack([np.asarray(Image.open(save / video / f'{t:05d}.png')) for t in range(1, T)])
+    return masks.astype(np.uint8)
+
+
 def default_palette():
     pal = [0, 0, 0, 128, 0, 0, 0, 128, 0, 128, 128, 0, 0, 0, 128, 128, 0, 128, 0, 128, 128,
            128, 128, 128, 64, 0, 0, 192, 0, 0, 64, 128, 0, 192, 128, 0]

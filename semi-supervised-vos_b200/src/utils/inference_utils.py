@@ -18,6 +18,7 @@ from src.model.predict import prepare_first_frame
 from src.utils.utils import save_predictions
 from vosb200 import PropagationEngine
 from vosb200.engine import precision_for, required_ring_slots
+from vosb200.sequence import nearest_index
 
 REDUCTIONS = {'maximum': lambda x, y: torch.maximum(x, y),
               'minimum': lambda x, y: torch.minimum(x, y),
@@ -103,17 +104,139 @@ def inference_single(model, inference_loader, total_len, annotation_dir, last_vi
         sink.flush()
 
 
-def _not_built(name):
-    def strategy(*args, **kwargs):
-        raise NotImplementedError(
-            f"inference strategy '{name}' (test-time augmentation, reference src/utils/inference_utils.py) is "
-            f"outside this round's hot-path scope (SURVEY.md section 8f, row N2); use --inference-strategy single")
-    strategy.__name__ = name
-    return strategy
+# ------------------------------------------------------------------------------------------------
+# Test-time-augmentation strategies (reference: src/utils/inference_utils.py:90-595).
+# Every strategy is "two propagation memories side by side + a per-frame fusion of their outputs"; the
+# memories never exchange labels.  Each memory is one PropagationEngine (own ring); the fusion runs on the
+# device on the tensors the reference fuses on the host, with the same torch calls (incl. its quirks:
+# `torch.fliplr` for BOTH flip strategies, src/utils/inference_utils.py:173,279; `fliplr` of a (1,d,H,W)
+# probability map flips the class axis; `.half()` before the arg-max).
+# ------------------------------------------------------------------------------------------------
+class _Stream:
+    """One propagation memory of a multi-stream strategy."""
+
+    def __init__(self, slots):
+        self.slots, self.engine = slots, None
+
+    def start(self, features, label_1hot, H, W, d):
+        (_, _, H_d, W_d) = features.shape
+        n_pixels = H_d * W_d
+        if self.engine is None or self.engine.max_pixels < n_pixels:
+            if self.engine is not None:
+                self.engine.close()
+            self.engine = PropagationEngine(max_pixels=n_pixels, ring_slots=max(self.slots, 48), device=features.device)
+        self.geom = (H_d, W_d, H, W, int(d))
+        self.engine.reset(H_d, W_d, H, W, int(d), precision_for(features.dtype))
+        self.engine.append(0, features)
+        self.engine.set_labels_index(0, label_1hot[:, 0].argmax(0))
+
+    def step(self, frame_idx, features, p, probability_propagation):
+        """-> (H,W) uint8 label map, or the (1,d,H,W) fp32 up-sampled prediction in probability mode."""
+        self.engine.append(frame_idx, features)
+        out = self.engine.step(frame_idx, p['frame_range'], p['ref_num'], p['sigma_1'], p['sigma_2'], p['temperature'],
+                               probability_propagation, want_prediction=probability_propagation, want_lowres=False,
+                               want_fullres=not probability_propagation)
+        if not probability_propagation:
+            return out['mask']
+        H_d, W_d, H, W, d = self.geom
+        ys, xs = nearest_index(H, H_d, features.device), nearest_index(W, W_d, features.device)
+        return out['prediction'].view(d, H_d, W_d)[:, ys][:, :, xs].unsqueeze(0)     # F.interpolate(mode='nearest')
 
 
-inference_hor_flip = _not_built('inference_hor_flip')
-inference_ver_flip = _not_built('inference_ver_flip')
-inference_2_scale = _not_built('inference_2_scale')
-inference_multimodel = _not_built('inference_multimodel')
-inference_3_scale = _not_built('inference_3_scale')
+def _fuse(pred_a, pred_b, probability_propagation, reduction_str):
+    """inference_utils.py:178-184 (and the same lines of the other strategies) -> (H,W) uint8 on the device."""
+    if probability_propagation:
+        fused = REDUCTIONS.get(reduction_str)(pred_a, pred_b).half()
+        return torch.argmax(fused, 1)[0].to(torch.uint8)
+    return torch.maximum(pred_a, pred_b)
+
+
+def _inference_two_streams(models, inference_loader, total_len, annotation_dir, last_video, save, sigma_1, sigma_2,
+                           frame_range, ref_num, temperature, probability_propagation, reduction_str, disable,
+                           strategy, scale=None, transform_b=None):
+    p = dict(sigma_1=sigma_1, sigma_2=sigma_2, frame_range=frame_range, ref_num=ref_num, temperature=temperature)
+    slots = required_ring_slots(frame_range, ref_num)
+    a, b = _Stream(slots), _Stream(slots)
+    frame_idx, sink = 0, None
+    for input, (current_video,) in tqdm(inference_loader, total=total_len, disable=disable):
+        if current_video != last_video:
+            if sink is not None:
+                sink.flush()
+                sink = None
+            frame_idx = 0
+        if strategy == 'multimodel':
+            input_a = input_b = input.to(Config.DEVICE, non_blocking=True)
+        else:
+            input_a, input_b = input[0].to(Config.DEVICE, non_blocking=True), input[1].to(Config.DEVICE, non_blocking=True)
+        with torch.autocast('cuda', dtype=torch.float16):
+            features_a, features_b = models[0](input_a), models[1](input_b)
+        if frame_idx == 0:
+            first_annotation = annotation_dir / current_video / '00000.png'
+            prepared = prepare_first_frame(current_video, save, first_annotation, sigma_1, sigma_2,
+                                           inference_strategy={'vert-flip': 'ver-flip'}.get(strategy, strategy),
+                                           probability_propagation=probability_propagation, scale=scale)
+            if strategy in ('hor-flip', 'vert-flip'):
+                label_a, label_b, d, palette = prepared[0], prepared[1], prepared[2], prepared[3]
+            elif strategy in ('2-scale', 'hor-2-scale'):
+                (label_a, label_b), d, palette = prepared[0], prepared[1], prepared[2]
+            else:   # multimodel: one label set for both models
+                label_a = label_b = prepared[0]
+                d, palette = prepared[1], prepared[2]
+            (_, _, H, W) = input_a.shape
+            a.start(features_a, label_a, H, W, d)
+            b.start(features_b, label_b, H, W, d)     # both memories predict at the size of the first input
+            sink = _VideoSink(current_video, palette, save, H, W, features_a.device)
+            frame_idx += 1
+            last_video = current_video
+            continue
+        pred_a = a.step(frame_idx, features_a, p, probability_propagation)
+        pred_b = b.step(frame_idx, features_b, p, probability_propagation)
+        if transform_b is not None:
+            pred_b = transform_b(pred_b)
+        sink.next_slot().copy_(_fuse(pred_a, pred_b, probability_propagation, reduction_str))
+        last_video = current_video
+        frame_idx += 1
+    if sink is not None:
+        sink.flush()
+
+
+def inference_hor_flip(model, inference_loader, total_len, annotation_dir, last_video, save, sigma_1, sigma_2,
+                       frame_range, ref_num, temperature, probability_propagation, reduction_str, disable):
+    """Reference: src/utils/inference_utils.py:90-192."""
+    _inference_two_streams((model, model), inference_loader, total_len, annotation_dir, last_video, save, sigma_1,
+                           sigma_2, frame_range, ref_num, temperature, probability_propagation, reduction_str, disable,
+                           'hor-flip', transform_b=torch.fliplr)
+
+
+def inference_ver_flip(model, inference_loader, total_len, annotation_dir, last_video, save, sigma_1, sigma_2,
+                       frame_range, ref_num, temperature, probability_propagation, reduction_str, disable):
+    """Reference: src/utils/inference_utils.py:195-298 -- which un-flips the vertical stream with `torch.fliplr`
+    (:279), i.e. horizontally; kept, because the drop-in must write the files the reference writes."""
+    _inference_two_streams((model, model), inference_loader, total_len, annotation_dir, last_video, save, sigma_1,
+                           sigma_2, frame_range, ref_num, temperature, probability_propagation, reduction_str, disable,
+                           'vert-flip', transform_b=torch.fliplr)
+
+
+def inference_2_scale(model, inference_loader, total_len, annotation_dir, last_video, save, sigma_1, sigma_2,
+                      frame_range, ref_num, temperature, probability_propagation, scale, reduction_str, flip_pred,
+                      disable):
+    """Reference: src/utils/inference_utils.py:302-410 ('2-scale', and 'hor-2-scale' with flip_pred)."""
+    hflip = (lambda t: torch.flip(t, dims=(-1,))) if flip_pred else None      # torchvision hflip: last axis
+    _inference_two_streams((model, model), inference_loader, total_len, annotation_dir, last_video, save, sigma_1,
+                           sigma_2, frame_range, ref_num, temperature, probability_propagation, reduction_str, disable,
+                           'hor-2-scale' if flip_pred else '2-scale', scale=scale, transform_b=hflip)
+
+
+def inference_multimodel(model, additional_model, inference_loader, total_len, annotation_dir, last_video, save,
+                         sigma_1, sigma_2, frame_range, ref_num, temperature, probability_propagation, reduction_str,
+                         disable):
+    """Reference: src/utils/inference_utils.py:411-511 (two networks, one input, one label set)."""
+    _inference_two_streams((model, additional_model), inference_loader, total_len, annotation_dir, last_video, save,
+                           sigma_1, sigma_2, frame_range, ref_num, temperature, probability_propagation, reduction_str,
+                           disable, 'multimodel')
+
+
+def inference_3_scale(*args, **kwargs):
+    raise NotImplementedError(
+        "inference strategy '3-scale' (reference src/utils/inference_utils.py:514-595) re-runs the whole loader at "
+        "scales 0.9 / 1.0 / s with a hard-coded (480, 910) output size; it is not built (SURVEY.md section 8f, row N2)")

@@ -73,3 +73,17 @@ def parse_case(key):
     parts = key.split('_')
     return dict(t=int(parts[0][1:]), ref_num=int(parts[1][1:]), frame_range=int(parts[2][1:]),
                 temperature=float(parts[3][1:]), prob=bool(int(parts[4][1:])))
+
+
+META_TTA = json.loads((GOLDEN / 'meta_tta.json').read_text())   # oracle/make_golden_tta.py
+TTA_NAMES = sorted(META_TTA)
+
+
+def tta_inputs(name):
+    """(cfg, feats_a, feats_b, first annotation, (H,W) of input B) exactly as oracle/make_golden_tta.py builds them."""
+    import sys
+    sys.path.insert(0, str(GOLDEN.parent.parent))
+    from oracle.make_golden_tta import streams
+    cfg = META_TTA[name]
+    feats_a, feats_b, first, size_b = streams(cfg['strategy'], cfg['T'], cfg['H'], cfg['W'], cfg['n_objects'], cfg['seed'])
+    return cfg, feats_a, feats_b, first, size_b

@@ -1,0 +1,92 @@
+"""GPU parity of the drop-in entry points themselves (semi-supervised-vos_b200/src/utils/inference_utils.py):
+`inference_single` and the two-stream test-time-augmentation loops, driven exactly like the reference's are driven by
+oracle/reference_harness.py -- a table-lookup model, a one-clip loader, an annotation PNG on disk -- and compared
+with the PNGs the REFERENCE wrote for the same inputs (tests/golden/seq_*.npz, tta_*.npz)."""
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from oracle import reference_harness as RH
+from tests import _golden as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _dataset(tmp_path, first, video='clip'):
+    ann_dir = tmp_path / 'Annotations' / '480p'
+    (ann_dir / video).mkdir(parents=True)
+    img = Image.fromarray(np.asarray(first).astype(np.uint8), mode='P')
+    img.putpalette(RH.default_palette())
+    img.save(ann_dir / video / '00000.png')
+    return ann_dir, tmp_path / 'out'
+
+
+def _read_masks(save, video, T):
+    return np.stack([np.asarray(Image.open(save / video / f'{t:05d}.png')) for t in range(1, T)]).astype(np.uint8)
+
+
+def _table(feats):
+    return lambda inp: feats[int(inp[0, 0, 0, 0].item())][None]
+
+
+@pytest.fixture()
+def mirror():
+    from src.config import Config
+    from src.utils import inference_utils as iu
+    old = Config.DEVICE
+    Config.DEVICE = torch.device('cuda', 0)
+    yield iu
+    Config.DEVICE = old
+
+
+@pytest.mark.parametrize('name', ['A_label_r9', 'B_prob_r5', 'F_wide_r9'])
+def test_inference_single_writes_the_reference_pngs(name, tmp_path, mirror):
+    feats, first, run = G.sequence_inputs(name)
+    masks_ref, _ = G.sequence_golden(name)
+    T, (H, W) = feats.shape[0], first.shape
+    ann_dir, save = _dataset(tmp_path, first)
+    loader = [(torch.full((1, 1, H, W), float(t)), ('clip',)) for t in range(T)]
+    with torch.no_grad():
+        mirror.inference_single(_table(feats.cuda()), loader, T, ann_dir, 'clip', str(save), run['sigma_1'], run['sigma_2'],
+                                run['frame_range'], run['ref_num'], run['temperature'], run['probability_propagation'], True)
+    masks = _read_masks(save, 'clip', T)
+    agree = float((masks == masks_ref).mean())
+    print(f'inference_single/{name}: mask agreement {agree:.6f}')
+    assert agree >= 0.999
+    assert np.array_equal(np.asarray(Image.open(save / 'clip' / '00000.png')), first)      # predict.py:120-126
+
+
+@pytest.mark.parametrize('name', G.TTA_NAMES)
+def test_two_stream_strategies_write_the_reference_pngs(name, tmp_path, mirror):
+    cfg, feats_a, feats_b, first, size_b = G.tta_inputs(name)
+    want = np.load(G.GOLDEN / f'tta_{name}.npz')['masks']
+    T, (H, W) = cfg['T'], first.shape
+    Hb, Wb = (H, W) if size_b is None else size_b
+    ann_dir, save = _dataset(tmp_path, first)
+    fa, fb = feats_a.cuda(), feats_b.cuda()
+    common = (T, ann_dir, 'clip', str(save), 8.0, 21.0, 40, 9, 1.0, cfg['probability_propagation'])
+    strategy = cfg['strategy']
+    with torch.no_grad():
+        if strategy == 'multimodel':
+            loader = [(torch.full((1, 1, H, W), float(t)), ('clip',)) for t in range(T)]
+            mirror.inference_multimodel(_table(fa), _table(fb), loader, *common, cfg['reduction'], True)
+        else:
+            loader = [([torch.full((1, 1, H, W), float(t)), torch.full((1, 1, Hb, Wb), float(t) + 0.25)], ('clip',))
+                      for t in range(T)]
+            model = lambda inp: (fb if float(inp[0, 0, 0, 0]) % 1 else fa)[int(inp[0, 0, 0, 0].item())][None]  # noqa: E731
+            if strategy == 'hor-flip':
+                mirror.inference_hor_flip(model, loader, *common, cfg['reduction'], True)
+            elif strategy == 'vert-flip':
+                mirror.inference_ver_flip(model, loader, *common, cfg['reduction'], True)
+            else:
+                mirror.inference_2_scale(model, loader, *common, cfg['scale'], cfg['reduction'], strategy == 'hor-2-scale', True)
+    masks = _read_masks(save, 'clip', T)
+    agree = float((masks == want).mean())
+    print(f'{strategy}/{name}: mask agreement {agree:.6f}')
+    assert agree >= 0.999
+
+
+def test_three_scale_names_the_missing_row(mirror):
+    with pytest.raises(NotImplementedError, match='3-scale'):
+        mirror.inference_3_scale()

@@ -86,6 +86,18 @@ def test_sequences_on_16bit_embeddings_match_reference(tag):
     assert np.array_equal(torch.stack(preds).numpy(), preds_ref)
 
 
+@pytest.mark.parametrize('name', G.TTA_NAMES)
+def test_two_stream_strategies_match_reference(name):
+    """hor-flip / vert-flip / 2-scale / hor-2-scale / multimodel: the reference's own loops (goldens) vs the
+    restatement, masks bit-exact."""
+    cfg, feats_a, feats_b, first, _ = G.tta_inputs(name)
+    got = O.propagate_two_streams(cfg['strategy'], feats_a, feats_b, first,
+                                  probability_propagation=cfg['probability_propagation'], reduction=cfg['reduction'],
+                                  scale=cfg['scale'])
+    want = np.load(G.GOLDEN / f'tta_{name}.npz')['masks']
+    assert np.array_equal(got.numpy(), want)
+
+
 def test_topk_extension_reduces_to_reference_when_k_covers_everything():
     feats, hist, _ = G.predict_case_inputs()
     t = 10
