@@ -59,6 +59,10 @@ def parse_args():
     ap.add_argument('--precision', choices=['f16', 'split3'], default='f16',
                     help='embeddings resident in HBM for `value`: fp16 (what VOSNet emits under autocast; one exact '
                          'tensor-core pass) or fp32 (bf16 hi+lo split, three passes)')
+    ap.add_argument('--lanes', type=int, default=1,
+                    help='sequences in flight per GPU (one engine + stream each; 2 gives +2-3 %% frames/s but the lanes\' small '
+                         'kernels delay the start of the other lane\'s fused kernel, so its per-launch time reads higher)')
+    ap.add_argument('--no-kernel-events', action='store_true', help='do not bracket every kernel with CUDA events (roofline fields become null)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ref-frames', type=int, default=2, help='reference arm: propagated frames per step')
@@ -69,6 +73,7 @@ def workload_config(args, n_gpus):
     return {'workload': f'synthetic DAVIS-2017-val-shaped shard: {args.clips} clips x {args.frames} frames per GPU, '
                         f'480x854 (60x107 stride-8 features, K=256), 2-4 objects',
             'clips_per_gpu': args.clips, 'frames_per_clip': args.frames, 'n_gpus': n_gpus,
+            'sequences_in_flight_per_gpu': max(1, min(args.lanes, args.clips)),
             'ref_num': REF_NUM, 'frame_range': FRAME_RANGE, 'sigma': [SIGMA_1, SIGMA_2], 'temperature': TEMPERATURE,
             'precision': ('fp16 embeddings (VOSNet under autocast, as the reference on CUDA): one tcgen05 kind::f16 pass, '
                           'products exact in the fp32 accumulator, fp32 softmax' if args.precision == 'f16' else
@@ -209,7 +214,7 @@ def run_ours(args, rank, world, local_rank):
     from vosb200 import PropagationEngine
     from vosb200 import synthetic
     from vosb200.pipeline import ClipSegmenter
-    from vosb200.sequence import propagate_clip
+    from vosb200.sequence import propagate_clip, propagate_clips_lanes
     from src.model.vos_net import VOSNet
 
     torch.cuda.set_device(local_rank)
@@ -229,20 +234,31 @@ def run_ours(args, rank, world, local_rank):
         clips = [(f.half(), first) for f, first in clips]
     passes = 1 if args.precision == 'f16' else 3
     P = clips[0][0].shape[2] * clips[0][0].shape[3]
-    eng = PropagationEngine(max_pixels=P, ring_slots=48, device=dev)
+    lanes = max(1, min(args.lanes, C))
+    engines = [PropagationEngine(max_pixels=P, ring_slots=48, device=dev) for _ in range(lanes)]
+    lane_streams = [torch.cuda.Stream(dev) for _ in range(lanes)]
+    eng = engines[0]
     masks_keep = [None] * C
 
     def prop_step():
-        for i, (feats, first) in enumerate(clips):
-            masks_keep[i] = propagate_clip(eng, feats, first, SIGMA_1, SIGMA_2, FRAME_RANGE, REF_NUM, TEMPERATURE,
-                                           False, d=n_obj[i] + 1)
+        if lanes == 1:
+            for i, (feats, first) in enumerate(clips):
+                masks_keep[i] = propagate_clip(eng, feats, first, SIGMA_1, SIGMA_2, FRAME_RANGE, REF_NUM, TEMPERATURE,
+                                               False, d=n_obj[i] + 1)
+        else:   # several sequences in flight: small kernels of one lane run under the affinity kernel of another
+            masks_keep[:] = propagate_clips_lanes(engines, [(f, first, n_obj[i] + 1) for i, (f, first) in enumerate(clips)],
+                                                  SIGMA_1, SIGMA_2, FRAME_RANGE, REF_NUM, TEMPERATURE, False,
+                                                  streams=lane_streams)
 
     for _ in range(args.warmup):
         prop_step()
     launches_per_step = 3 * (T - 1) + 3        # per clip: reset + append(0) + labels(0) + (append, affinity, merge) per frame
-    eng.enable_timing(args.steps * C * launches_per_step + 16)
+    # inside the timed region only the dominant kernel (fused affinity) is bracketed with events: event records cost
+    # front-end time (all three classes: -6 % frames/s); append / merge are timed in one extra pass afterwards
+    for e_ in engines:
+        e_.enable_timing(0 if args.no_kernel_events else args.steps * C * launches_per_step + 16, classes=('affinity',))
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = eng.launch_count
+    launches0 = sum(e_.launch_count for e_ in engines)
     barrier()
     with ClockSampler(local_rank) as clocks:
         ev0.record()
@@ -251,9 +267,19 @@ def run_ours(args, rank, world, local_rank):
         ev1.record()
         barrier()
     ms = ev0.elapsed_time(ev1)
-    gpu_launches = eng.launch_count - launches0
-    stage = eng.read_timing()
-    eng.enable_timing(0)
+    gpu_launches = sum(e_.launch_count for e_ in engines) - launches0
+    stage = {'append': (0.0, 0), 'affinity': (0.0, 0), 'merge': (0.0, 0)}
+    for e_ in engines:
+        for k_, (ms_, n_) in e_.read_timing().items():
+            stage[k_] = (stage[k_][0] + ms_, stage[k_][1] + n_)
+        e_.enable_timing(0)
+    if not args.no_kernel_events:
+        eng.enable_timing(launches_per_step + 16, classes=('append', 'merge'))
+        propagate_clip(eng, clips[0][0], clips[0][1], SIGMA_1, SIGMA_2, FRAME_RANGE, REF_NUM, TEMPERATURE, False, d=n_obj[0] + 1)
+        torch.cuda.synchronize(dev)
+        for k_, (ms_, n_) in eng.read_timing().items():
+            stage[k_] = (stage[k_][0] + ms_, stage[k_][1] + n_)
+        eng.enable_timing(0)
     t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)

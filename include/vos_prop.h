@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define VOSPROP_ABI_VERSION 2
+#define VOSPROP_ABI_VERSION 3
 #define VOSPROP_MAX_REFS 32     /* reference frames per step (reference default ref_num = 9)   */
 #define VOSPROP_MAX_CLASSES 14  /* d = objects + 1 (DAVIS <= 11, YouTube-VOS <= 11)            */
 #define VOSPROP_FEAT_DIM 256    /* VOSNet embedding width, src/model/vos_net.py:22             */
@@ -83,6 +83,12 @@ typedef struct vosprop_step {
     uint8_t* out_mask_fullres;               /* device (H, W) uint8 or NULL -- nearest up-sample + argmax (inference_utils.py:74-75) */
     int32_t* out_topk_idx;                   /* device (P, topk) int32 or NULL (top-k mode only): reference indices r*P + pixel
                                                 (r = position in ref_frames), best first; -1 where fewer than k exist         */
+    /* Several sequences in flight on one GPU (one engine + one stream each): the fused affinity kernel fills every SM,
+     * so the affinity kernels of different sequences cannot overlap each other.  Chaining them with these two events
+     * keeps them back to back on the device while the launch latencies, appends and merges of the other sequences
+     * fill the gaps between them.  Both may be NULL. */
+    void* wait_event;                        /* cudaEvent_t: the stream waits for it before the affinity kernel  */
+    void* record_event;                      /* cudaEvent_t: recorded right after the affinity kernel            */
 } vosprop_step;
 
 const char* vosprop_last_error(void);
@@ -151,6 +157,9 @@ int64_t vosprop_launch_count(const vosprop_engine* e);
  * totals_ms[3] / counts[3] are indexed by enum vosprop_timed_kernel. */
 enum vosprop_timed_kernel { VOSPROP_T_APPEND = 0, VOSPROP_T_AFFINITY = 1, VOSPROP_T_MERGE = 2 };
 int vosprop_timing_enable(vosprop_engine* e, int32_t capacity);
+/* Which kernel classes get event pairs: bit (1 << vosprop_timed_kernel); default all three.  Event records cost a few
+ * microseconds of front-end time per frame, so bench.py times only the dominant kernel inside its timed region. */
+int vosprop_timing_select(vosprop_engine* e, int32_t class_mask);
 int vosprop_timing_read(vosprop_engine* e, double* totals_ms, int64_t* counts);
 
 #ifdef __cplusplus

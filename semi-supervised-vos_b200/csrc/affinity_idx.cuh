@@ -301,6 +301,12 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, float (&v)[16
 }
 
 constexpr int kQC = 16;   // columns per epilogue step
+#ifndef VOS_POLY_EVERY
+#define VOS_POLY_EVERY 0
+#endif
+constexpr int kPolyEvery = VOS_POLY_EVERY;   // fast tile path: 1 of kPolyEvery column pairs uses the polynomial exp2 (0: none).
+// Measured (480p, R = 9, F16): 0 -> 225 us, 4 -> 234 us, 2 -> 242 us per launch: the epilogue warps are bound by their own
+// instruction latency, not by the MUFU pipe, so trading one MUFU for ~7 FMA/ALU instructions loses.  Kept for the record.
 
 __device__ __forceinline__ float max16(const float (&v)[kQC]) {
     const float a = fmax3(v[0], v[1], v[2]), b = fmax3(v[3], v[4], v[5]), c = fmax3(v[6], v[7], v[8]);
@@ -487,8 +493,10 @@ __device__ __forceinline__ void fast_tile32(RowAcc<D>& st, float (&va)[kQC], flo
         for (int j = 0; j < kQC; j += 2) {
             const float2 ea = ffma2(make_float2(va[j], va[j + 1]), s2, nm2);
             const float2 eb = ffma2(make_float2(vb[j], vb[j + 1]), s2, nm2);
-            const float2 pa = make_float2(ex2(ea.x), ex2(ea.y));
-            const float2 pb = make_float2(ex2(eb.x), ex2(eb.y));
+            // every kPolyEvery-th column pair takes its exponentials from the FMA pipe (ex2_poly2): the MUFU is the
+            // busiest pipe of this kernel (58 % in the v10 capture), the FMA pipe has room
+            const float2 pa = (kPolyEvery && (j / 2) % kPolyEvery == kPolyEvery - 1) ? ex2_poly2(ea) : make_float2(ex2(ea.x), ex2(ea.y));
+            const float2 pb = (kPolyEvery && (j / 2) % kPolyEvery == 1 % kPolyEvery) ? ex2_poly2(eb) : make_float2(ex2(eb.x), ex2(eb.y));
             l2 = fadd2(l2, fadd2(pa, pb));
             const float2 wa = fmul2(pa, Ga), wb = fmul2(pb, Gb);
             suma = fadd2(suma, wa);
@@ -544,7 +552,9 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                  const __grid_constant__ AffinityParams prm) {
     using Cfg = IdxCfg<kSplit>;
     extern __shared__ uint8_t smem_raw[];
+    pdl_launch_dependents();
     const IdxPipe pp = idx_setup<Cfg::kGroup, Cfg::kStages>(smem_raw, &tmap_hi, &tmap_lo, Cfg::kAccBufs, kIdxEpiWarps);
+    pdl_wait();       // barriers, TMEM and tensor-map prefetch are set up while the append kernel before us drains
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const vosd::Decomp dec = vosd::make_decomp(prm.n_pixels, prm.n_refs, prm.num_sms);

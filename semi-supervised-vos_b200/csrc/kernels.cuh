@@ -504,6 +504,8 @@ constexpr int kMergeLanes = 8;        // lanes cooperating on one target pixel
 
 __global__ void __launch_bounds__(kMergeThreads) vos_merge_writeback(const MergeParams prm) {
     extern __shared__ uint8_t row_cls[];  // [w_lowres]
+    pdl_launch_dependents();
+    pdl_wait();                           // the affinity kernel's partials (and everything before it) are complete
     const int y = blockIdx.x;
     const int sublane = threadIdx.x & (kMergeLanes - 1);
     const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~(kMergeLanes - 1));   // the 8 lanes of this pixel group
@@ -611,6 +613,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) vos_append_nchw(const T* __restrict__ src, __nv_bfloat16* __restrict__ hi,
                                                        __nv_bfloat16* __restrict__ lo, int n_pixels, size_t slot_row0, int fmt) {
     __shared__ float tile[64][33];
+    pdl_launch_dependents();
+    pdl_wait();                           // the ring slot being overwritten is no longer read by earlier kernels
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int p = p0 + lane;
@@ -639,6 +643,8 @@ __global__ void __launch_bounds__(256) vos_append_nchw(const T* __restrict__ src
 template <typename T>
 __global__ void __launch_bounds__(256) vos_append_nhwc8(const T* __restrict__ src, __nv_bfloat16* __restrict__ hi,
                                                         __nv_bfloat16* __restrict__ lo, int n_pixels, size_t slot_row0, int fmt) {
+    pdl_launch_dependents();
+    pdl_wait();
     const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;  // group of 8 channels
     if (i >= static_cast<size_t>(n_pixels) * (kK / 8)) return;
     float x[8];
@@ -664,6 +670,8 @@ __global__ void __launch_bounds__(256) vos_append_nhwc8(const T* __restrict__ sr
 template <typename T>
 __global__ void __launch_bounds__(256) vos_append_nhwc(const T* __restrict__ src, __nv_bfloat16* __restrict__ hi,
                                                        __nv_bfloat16* __restrict__ lo, int n_pixels, size_t slot_row0, int fmt) {
+    pdl_launch_dependents();
+    pdl_wait();
     const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;  // channel pair index
     if (i >= static_cast<size_t>(n_pixels) * (kK / 2)) return;
     uint32_t lo_bits = 0;

@@ -234,6 +234,10 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- math
 // packed fp32 pairs (FFMA2 / FADD2 on sm_100): two lanes of work per issue slot
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
@@ -261,6 +265,28 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {  // FMNMX3
     float d;
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
     return d;
+}
+// 2^x for a pair of x <= 0 on the FMA / ALU pipes instead of the MUFU (the trick of FlashAttention-4): round to the
+// nearest integer with the 1.5*2^23 magic constant, degree-5 polynomial for 2^f on [-0.5, 0.5] (relative error < 3e-6),
+// exponent added as an integer.  Inputs below -126 (incl. -inf) give 0 like ex2.approx.ftz.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+    const float kMagic = 12582912.f;
+    x.x = fmaxf(x.x, -127.f);
+    x.y = fmaxf(x.y, -127.f);
+    const float2 r = fadd2(x, make_float2(kMagic, kMagic));
+    const float2 n = fadd2(r, make_float2(-kMagic, -kMagic));
+    const float2 f = fadd2(x, make_float2(-n.x, -n.y));
+    float2 p = ffma2(f, make_float2(1.33335581e-3f, 1.33335581e-3f), make_float2(9.61812911e-3f, 9.61812911e-3f));
+    p = ffma2(p, f, make_float2(5.55041087e-2f, 5.55041087e-2f));
+    p = ffma2(p, f, make_float2(2.40226507e-1f, 2.40226507e-1f));
+    p = ffma2(p, f, make_float2(6.93147182e-1f, 6.93147182e-1f));
+    p = ffma2(p, f, make_float2(1.f, 1.f));
+    float2 out;
+    out.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(r.x) << 23));
+    out.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(r.y) << 23));
+    if (x.x <= -127.f) out.x = 0.f;
+    if (x.y <= -127.f) out.y = 0.f;
+    return out;
 }
 __device__ __forceinline__ float ex2(float x) {  // MUFU.EX2, flushes denormals, ex2(-inf) = 0
     float y;

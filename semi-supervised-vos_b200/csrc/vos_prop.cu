@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "decompose.h"
@@ -81,13 +82,29 @@ struct vosprop_engine {
     std::vector<int> ev_kind;
     size_t ev_used = 0;
     bool timing = false;
+    int timing_mask = 7;
 };
 
 namespace {
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream is still running;
+// every kernel launched this way executes griddepcontrol.wait (vosptx::pdl_wait) before it touches memory the
+// predecessor writes, and griddepcontrol.launch_dependents at its start.  This hides the ~5 us launch gaps between the
+// three kernels of a frame (append -> fused affinity -> merge), 6 % of a 480p frame.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
 struct TimedLaunch {   // RAII: records an event pair around one kernel launch when timing is on
     vosprop_engine* e; cudaStream_t st; bool on;
     TimedLaunch(vosprop_engine* e_, int kind, cudaStream_t st_) : e(e_), st(st_), on(false) {
-        if (e->timing && e->ev_used + 2 <= e->ev.size()) {
+        if (e->timing && ((e->timing_mask >> kind) & 1) && e->ev_used + 2 <= e->ev.size()) {
             on = true;
             e->ev_kind[e->ev_used / 2] = kind;
             cudaEventRecord(e->ev[e->ev_used], st);
@@ -122,10 +139,10 @@ template <int D>
 int launch_affinity(vosprop_engine* e, const vosk::AffinityParams& prm, int grid, int kernel, cudaStream_t st) {
     if (kernel == VOSPROP_KERNEL_TC && prm.feat_fmt == vosk::kFmtSplit) {
         VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_idx<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kIdxSmem));
-        vosk::vos_affinity_idx<D, true><<<grid, vosk::kIdxThreads, vosk::kIdxSmem, st>>>(e->tmap_hi, e->tmap_lo, prm);
+        VOS_CUDA(launch_pdl(vosk::vos_affinity_idx<D, true>, grid, vosk::kIdxThreads, vosk::kIdxSmem, st, e->tmap_hi, e->tmap_lo, prm));
     } else if (kernel == VOSPROP_KERNEL_TC) {
         VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_idx<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kIdxSmem));
-        vosk::vos_affinity_idx<D, false><<<grid, vosk::kIdxThreads, vosk::kIdxSmem, st>>>(e->tmap_hi, e->tmap_lo, prm);
+        VOS_CUDA(launch_pdl(vosk::vos_affinity_idx<D, false>, grid, vosk::kIdxThreads, vosk::kIdxSmem, st, e->tmap_hi, e->tmap_lo, prm));
     } else if (kernel == VOSPROP_KERNEL_TC_DENSE) {
         VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kSmemTc));
         vosk::vos_affinity_tc<D><<<grid, vosk::kTcThreads, vosk::kSmemTc, st>>>(e->tmap_hi, e->tmap_lo, prm);
@@ -194,6 +211,7 @@ int propagate_topk(vosprop_engine* e, const vosprop_step* s, vosk::AffinityParam
         }
         VOS_CUDA(cudaGetLastError());
     }
+    if (s->record_event) VOS_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->record_event), st));
     vosk::TopkFinishParams fp{};
     vosk::MergeParams& mp = fp.mp;
     const int q_slot = ap.q_slot;
@@ -354,20 +372,20 @@ int vosprop_append_features(vosprop_engine* e, int32_t frame_idx, const void* fe
     TimedLaunch timed(e, VOSPROP_T_APPEND, st);
     if (layout == VOSPROP_NCHW) {
         const dim3 grid((P + 31) / 32, vosk::kK / 64);
-        if (dtype == VOSPROP_F32) vosk::vos_append_nchw<float><<<grid, 256, 0, st>>>(static_cast<const float*>(features), e->ring_hi, e->ring_lo, P, row0, fmt);
-        else if (dtype == VOSPROP_F16) vosk::vos_append_nchw<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(features), e->ring_hi, e->ring_lo, P, row0, fmt);
-        else vosk::vos_append_nchw<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(features), e->ring_hi, e->ring_lo, P, row0, fmt);
+        if (dtype == VOSPROP_F32) VOS_CUDA(launch_pdl(vosk::vos_append_nchw<float>, grid, 256, 0, st, static_cast<const float*>(features), e->ring_hi, e->ring_lo, P, row0, fmt));
+        else if (dtype == VOSPROP_F16) VOS_CUDA(launch_pdl(vosk::vos_append_nchw<__half>, grid, 256, 0, st, static_cast<const __half*>(features), e->ring_hi, e->ring_lo, P, row0, fmt));
+        else VOS_CUDA(launch_pdl(vosk::vos_append_nchw<__nv_bfloat16>, grid, 256, 0, st, static_cast<const __nv_bfloat16*>(features), e->ring_hi, e->ring_lo, P, row0, fmt));
     } else if (layout == VOSPROP_NHWC) {
         if (reinterpret_cast<uintptr_t>(features) % 16 == 0) {
             const unsigned grid = static_cast<unsigned>((static_cast<size_t>(P) * (vosk::kK / 8) + 255) / 256);
-            if (dtype == VOSPROP_F32) vosk::vos_append_nhwc8<float><<<grid, 256, 0, st>>>(static_cast<const float*>(features), e->ring_hi, e->ring_lo, P, row0, fmt);
-            else if (dtype == VOSPROP_F16) vosk::vos_append_nhwc8<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(features), e->ring_hi, e->ring_lo, P, row0, fmt);
-            else vosk::vos_append_nhwc8<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(features), e->ring_hi, e->ring_lo, P, row0, fmt);
+            if (dtype == VOSPROP_F32) VOS_CUDA(launch_pdl(vosk::vos_append_nhwc8<float>, grid, 256, 0, st, static_cast<const float*>(features), e->ring_hi, e->ring_lo, P, row0, fmt));
+            else if (dtype == VOSPROP_F16) VOS_CUDA(launch_pdl(vosk::vos_append_nhwc8<__half>, grid, 256, 0, st, static_cast<const __half*>(features), e->ring_hi, e->ring_lo, P, row0, fmt));
+            else VOS_CUDA(launch_pdl(vosk::vos_append_nhwc8<__nv_bfloat16>, grid, 256, 0, st, static_cast<const __nv_bfloat16*>(features), e->ring_hi, e->ring_lo, P, row0, fmt));
         } else {
             const unsigned grid = static_cast<unsigned>((static_cast<size_t>(P) * (vosk::kK / 2) + 255) / 256);
-            if (dtype == VOSPROP_F32) vosk::vos_append_nhwc<float><<<grid, 256, 0, st>>>(static_cast<const float*>(features), e->ring_hi, e->ring_lo, P, row0, fmt);
-            else if (dtype == VOSPROP_F16) vosk::vos_append_nhwc<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(features), e->ring_hi, e->ring_lo, P, row0, fmt);
-            else vosk::vos_append_nhwc<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(features), e->ring_hi, e->ring_lo, P, row0, fmt);
+            if (dtype == VOSPROP_F32) VOS_CUDA(launch_pdl(vosk::vos_append_nhwc<float>, grid, 256, 0, st, static_cast<const float*>(features), e->ring_hi, e->ring_lo, P, row0, fmt));
+            else if (dtype == VOSPROP_F16) VOS_CUDA(launch_pdl(vosk::vos_append_nhwc<__half>, grid, 256, 0, st, static_cast<const __half*>(features), e->ring_hi, e->ring_lo, P, row0, fmt));
+            else VOS_CUDA(launch_pdl(vosk::vos_append_nhwc<__nv_bfloat16>, grid, 256, 0, st, static_cast<const __nv_bfloat16*>(features), e->ring_hi, e->ring_lo, P, row0, fmt));
         }
     } else {
         return fail(VOSPROP_ERR_INVALID, "unknown layout %d", layout);
@@ -464,12 +482,14 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     if (static_cast<size_t>(dec.grid) * dec.max_segs * vosk::kIdxSub > e->partial_records)
         return fail(VOSPROP_ERR_UNSUPPORTED, "partial buffer too small (grid %d x segs %d)", dec.grid, dec.max_segs);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (s->wait_event) VOS_CUDA(cudaStreamWaitEvent(st, static_cast<cudaEvent_t>(s->wait_event), 0));
     if (s->topk > 0) return propagate_topk(e, s, ap, dec, st);
     {
         TimedLaunch timed(e, VOSPROP_T_AFFINITY, st);
         rc = dispatch_affinity(e, ap, dec.grid, kernel, st);
     }
     if (rc) return rc;
+    if (s->record_event) VOS_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->record_event), st));
 
     vosk::MergeParams mp{};
     mp.n_pixels = e->P; mp.p_pad = e->p_pad; mp.w_lowres = e->W_d; mp.h_lowres = e->H_d; mp.n_refs = s->n_refs;
@@ -491,7 +511,7 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     mp.out_prediction = s->out_prediction; mp.out_mask_lowres = s->out_mask_lowres; mp.out_mask_fullres = s->out_mask_fullres;
     {
         TimedLaunch timed(e, VOSPROP_T_MERGE, st);
-        vosk::vos_merge_writeback<<<e->H_d, vosk::kMergeThreads, e->W_d, st>>>(mp);
+        VOS_CUDA(launch_pdl(vosk::vos_merge_writeback, e->H_d, vosk::kMergeThreads, e->W_d, st, mp));
     }
     VOS_CUDA(cudaGetLastError());
     if (s->write_labels) e->slot_labels[q_slot] = s->probability_propagation ? 2 : 1;
@@ -578,6 +598,12 @@ int vosprop_timing_enable(vosprop_engine* e, int32_t capacity) {
     e->ev_kind.resize(e->ev.size() / 2);
     e->ev_used = 0;
     e->timing = capacity > 0;
+    return VOSPROP_OK;
+}
+
+int vosprop_timing_select(vosprop_engine* e, int32_t class_mask) {
+    if (!e) return fail(VOSPROP_ERR_INVALID, "null engine");
+    e->timing_mask = class_mask;
     return VOSPROP_OK;
 }
 

@@ -12,7 +12,7 @@ F32, F16, BF16 = 0, 1, 2
 NCHW, NHWC = 0, 1
 KERNEL_TC, KERNEL_SIMT, KERNEL_TC_DENSE = 0, 1, 2
 PREC_SPLIT3, PREC_F16, PREC_BF16 = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4
 
 LIB_PATH = Path(__file__).resolve().parent.parent / 'csrc' / 'libvosprop.so'
@@ -29,7 +29,8 @@ class Step(C.Structure):
                 ('temperature', C.c_float), ('probability_propagation', C.c_int32),
                 ('write_labels', C.c_int32), ('topk', C.c_int32), ('kernel', C.c_int32),
                 ('out_prediction', C.c_void_p), ('out_mask_lowres', C.c_void_p),
-                ('out_mask_fullres', C.c_void_p), ('out_topk_idx', C.c_void_p)]
+                ('out_mask_fullres', C.c_void_p), ('out_topk_idx', C.c_void_p),
+                ('wait_event', C.c_void_p), ('record_event', C.c_void_p)]
 
 
 class VosPropError(RuntimeError):
@@ -58,6 +59,7 @@ EXPORTS = {
     'vosprop_debug_clocks': (C.c_int, [C.c_void_p, C.c_void_p]),
     'vosprop_launch_count': (C.c_int64, [C.c_void_p]),
     'vosprop_timing_enable': (C.c_int, [C.c_void_p, C.c_int32]),
+    'vosprop_timing_select': (C.c_int, [C.c_void_p, C.c_int32]),
     'vosprop_timing_read': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
 

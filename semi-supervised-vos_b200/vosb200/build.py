@@ -31,7 +31,7 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not is_stale():
         return LIB
-    cmd = [find_nvcc(), *NVCC_FLAGS, '-o', str(LIB), *SOURCES]
+    cmd = [find_nvcc(), *NVCC_FLAGS, *os.environ.get('VOS_NVCC_DEFS', '').split(), '-o', str(LIB), *SOURCES]
     if verbose:
         cmd.insert(1, '-Xptxas=-v')
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)

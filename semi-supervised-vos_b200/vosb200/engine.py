@@ -91,8 +91,10 @@ class PropagationEngine:
     def launch_count(self) -> int:
         return self._lib.vosprop_launch_count(self._h)
 
-    def enable_timing(self, capacity: int):
-        """Bracket every kernel launch with CUDA events (bench.py roofline); 0 disables."""
+    def enable_timing(self, capacity: int, classes=('append', 'affinity', 'merge')):
+        """Bracket the kernel launches of the given classes with CUDA events (bench.py roofline); 0 disables."""
+        mask = sum(1 << ('append', 'affinity', 'merge').index(c) for c in classes)
+        capi.check(self._lib.vosprop_timing_select(self._h, mask))
         capi.check(self._lib.vosprop_timing_enable(self._h, int(capacity)))
 
     def read_timing(self):
@@ -152,7 +154,8 @@ class PropagationEngine:
                   kernel: int = capi.KERNEL_TC, want_prediction: bool = True, want_lowres: bool = True,
                   want_fullres: bool = True, out_fullres: Optional[torch.Tensor] = None,
                   out_prediction: Optional[torch.Tensor] = None, topk: int = 0,
-                  want_topk_idx: bool = False) -> Dict[str, torch.Tensor]:
+                  want_topk_idx: bool = False, wait_event: Optional[torch.cuda.Event] = None,
+                  record_event: Optional[torch.cuda.Event] = None) -> Dict[str, torch.Tensor]:
         """One propagation step.  topk = 0 is the reference (softmax over every reference pixel); topk = k in
         1..MAX_TOPK is the top-k extension (softmax over the k largest logits per target pixel), optionally
         returning the (P, k) reference indices r*P + pixel, best first."""
@@ -192,6 +195,10 @@ class PropagationEngine:
             tk = torch.empty((P, topk), dtype=torch.int32, device=self.device)
             st.out_topk_idx = tk.data_ptr()
             out['topk_idx'] = tk
+        if wait_event is not None:      # chain the affinity kernels of several sequences in flight (vos_prop.h)
+            st.wait_event = wait_event.cuda_event
+        if record_event is not None:
+            st.record_event = record_event.cuda_event
         capi.check(self._lib.vosprop_propagate(self._h, C.byref(st), self._stream()))
         return out
 

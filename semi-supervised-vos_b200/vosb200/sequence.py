@@ -2,7 +2,7 @@
 src/utils/inference_utils.py:27-83, with the feature extractor factored out)."""
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -68,3 +68,57 @@ def propagate_clip(engine: PropagationEngine, features: torch.Tensor, first_labe
                     kernel=kernel, want_prediction=False, want_lowres=False, want_fullres=False,
                     out_fullres=masks[t - 1], out_prediction=preds[t - 1] if return_predictions else None, topk=topk)
     return (masks, preds) if return_predictions else masks
+
+
+def propagate_clips_lanes(engines: Sequence[PropagationEngine], clips, sigma_1: float = 8.0, sigma_2: float = 21.0,
+                          frame_range: int = 40, ref_num: int = 9, temperature: float = 1.0,
+                          probability_propagation: bool = False, kernel: int = capi.KERNEL_TC, topk: int = 0,
+                          streams: Optional[Sequence[torch.cuda.Stream]] = None):
+    """Several sequences in flight on one GPU: clip i runs on lane i % len(engines) (one engine + one stream per lane).
+
+    Frames inside a sequence are strictly serial (the labels of frame t feed frame t+1), and the fused affinity kernel
+    of one sequence fills every SM.  The lanes advance round-robin, one frame each, and their affinity kernels are
+    chained through events (vosprop_step.wait_event / record_event) so they run back to back on the device while the
+    other lanes' launch latencies and small kernels fill the gaps.  (The small kernels do not co-reside with a resident
+    affinity CTA today: 5 of its 18 warps x 96 registers fill two of the four scheduler partitions' register files.)  clips: [(features (T,K,H_d,W_d), first annotation (H,W), d or None), ...].
+    Returns one (T-1,H,W) uint8 device tensor per clip.  No host sync inside; the current stream waits for the lanes."""
+    n_lanes = len(engines)
+    dev = engines[0].device
+    main = torch.cuda.current_stream(dev)
+    streams = list(streams) if streams is not None else [torch.cuda.Stream(dev) for _ in range(n_lanes)]
+    events = [torch.cuda.Event() for _ in range(n_lanes)]
+    for s, ev in zip(streams, events):
+        s.wait_stream(main)
+        ev.record(s)                      # creates the CUDA event behind torch's lazy wrapper
+    lanes = [[i for i in range(len(clips)) if i % n_lanes == lane] for lane in range(n_lanes)]
+    outs = [None] * len(clips)
+    cursor = [[0, 0] for _ in range(n_lanes)]         # per lane: (position in its clip list, next frame)
+    prev_event = None
+    busy = True
+    while busy:
+        busy = False
+        for lane in range(n_lanes):
+            pos, t = cursor[lane]
+            if pos >= len(lanes[lane]):
+                continue
+            busy = True
+            ci = lanes[lane][pos]
+            feats, first, d = clips[ci]
+            eng = engines[lane]
+            with torch.cuda.stream(streams[lane]):
+                if t == 0:
+                    first_t = torch.as_tensor(np.asarray(first)) if not torch.is_tensor(first) else first
+                    start_sequence(eng, feats[0], first_t, d)
+                    H, W = first_t.shape
+                    outs[ci] = torch.empty((feats.shape[0] - 1, H, W), dtype=torch.uint8, device=dev)
+                else:
+                    eng.append(t, feats[t])
+                    eng.step(t, frame_range, ref_num, sigma_1, sigma_2, temperature, probability_propagation, kernel=kernel,
+                             want_prediction=False, want_lowres=False, want_fullres=False, out_fullres=outs[ci][t - 1],
+                             topk=topk, wait_event=prev_event, record_event=events[lane])
+                    prev_event = events[lane]
+            t += 1
+            cursor[lane] = [pos + 1, 0] if t == feats.shape[0] else [pos, t]
+    for s in streams:
+        main.wait_stream(s)
+    return outs

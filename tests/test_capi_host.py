@@ -30,13 +30,13 @@ def test_exports_every_declared_symbol(lib):
     assert declared == set(_capi.EXPORTS), declared ^ set(_capi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.vosprop_abi_version() == 2
+    assert lib.vosprop_abi_version() == 3
 
 
 def test_struct_layout_matches_header(lib):
     from vosb200 import _capi
-    # int32 x2, int32[32], float[32], float, int32 x4, 4 pointers
-    assert C.sizeof(_capi.Step) == 8 + 128 + 128 + 4 + 16 + 4 + 32  # incl. 4 bytes padding before pointers
+    # int32 x2, int32[32], float[32], float, int32 x4, 6 pointers
+    assert C.sizeof(_capi.Step) == 8 + 128 + 128 + 4 + 16 + 4 + 48  # incl. 4 bytes padding before pointers
     assert C.sizeof(_capi.Config) == 16
 
 

@@ -122,3 +122,20 @@ def test_clips_of_different_geometry_through_one_engine():
         assert agree >= MASK_AGREE
         if agree == 1.0:
             assert err <= PROB_ATOL
+
+
+def test_lanes_give_the_same_masks_as_one_sequence_at_a_time():
+    """Three clips of different geometry on two lanes (two engines, two streams, chained affinity kernels) against the
+    same clips propagated one after the other."""
+    from vosb200.sequence import propagate_clip, propagate_clips_lanes
+    specs = ((12, 136, 264, 2, 81), (9, 160, 320, 3, 82), (15, 136, 264, 1, 83))
+    clips = []
+    for (T, H, W, n_obj, seed) in specs:
+        feats, first = O.synthetic_sequence(T, H, W, n_obj, seed=seed, feat_scale=0.30)
+        clips.append((feats.half().cuda(), first, None))
+    engines = [_engine(20 * 40), _engine(20 * 40)]
+    got = propagate_clips_lanes(engines, clips)
+    torch.cuda.synchronize()
+    for (feats, first, _), g in zip(clips, got):
+        want = propagate_clip(_engine(20 * 40), feats, first)
+        assert torch.equal(g, want)
