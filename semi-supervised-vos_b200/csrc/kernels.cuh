@@ -105,7 +105,8 @@ struct RowAcc {
 
 // Consumes 32 logits v[0..31] of reference pixels whose meta records start at `meta_col`
 // (16 floats each).  `n_valid`: number of leading valid columns (>= 32 when kPartial is false).
-template <int D, bool kPartial>
+// kPrior = false: no spatial prior (coef == 0: probability propagation, predict.py:58) -- one exp2 per logit.
+template <int D, bool kPartial, bool kPrior = true>
 __device__ __forceinline__ void consume32(RowAcc<D>& st, float (&v)[32], const float4* __restrict__ meta_col,
                                           int n_valid, float scale2, float coef, float rm, float xm) {
     if (kPartial) {
@@ -132,10 +133,13 @@ __device__ __forceinline__ void consume32(RowAcc<D>& st, float (&v)[32], const f
         if (kPartial && j >= n_valid) e = -INFINITY;
         const float p = ex2(e);
         st.l += p;
-        const float dr = a.x - rm;
-        const float dx = a.y - xm;
-        const float d2 = fmaf(dx, dx, dr * dr);
-        const float pw = ex2(fmaf(d2, -coef, e));
+        float pw = p;
+        if (kPrior) {
+            const float dr = a.x - rm;
+            const float dx = a.y - xm;
+            const float d2 = fmaf(dx, dx, dr * dr);
+            pw = ex2(fmaf(d2, -coef, e));
+        }
         st.acc[0] = fmaf(pw, a.z, st.acc[0]);
         if (D > 1) st.acc[1] = fmaf(pw, a.w, st.acc[1]);
         if (D > 2) {
@@ -213,8 +217,8 @@ vos_affinity_tc(const __grid_constant__ CUtensorMap tmap_hi, const __grid_consta
         for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(q_full, 1);
         mbar_init(q_empty, 1);
-        for (int i = 0; i < kAccBufs; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiThreads); }
-        for (int i = 0; i < kMetaStages; ++i) { mbar_init(&meta_full[i], 1); mbar_init(&meta_empty[i], kEpiThreads); }
+        for (int i = 0; i < kAccBufs; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiThreads / 32); }
+        for (int i = 0; i < kMetaStages; ++i) { mbar_init(&meta_full[i], 1); mbar_init(&meta_empty[i], kEpiThreads / 32); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -354,17 +358,22 @@ vos_affinity_tc(const __grid_constant__ CUtensorMap tmap_hi, const __grid_consta
                 tmem_ld_32x32b_x32(taddr + 32, v1);
                 tmem_ld_wait();
                 tc_fence_before_sync();
-                mbar_arrive(&acc_empty[buf]);                 // accumulator drained into registers
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);  // accumulator drained into registers (one arrival per warp)
                 mbar_wait(&meta_full[ms], mph);
                 const float4* mcol = meta_smem + ms * (kMetaTileBytes / 16) + half * 64 * (kMetaFloats / 4);
-                if (n_valid >= 64) {
+                if (n_valid >= 64 && coef == 0.f) {
+                    consume32<D, false, false>(st, v0, mcol, 32, prm.scale2, coef, rm, xm);
+                    consume32<D, false, false>(st, v1, mcol + 32 * (kMetaFloats / 4), 32, prm.scale2, coef, rm, xm);
+                } else if (n_valid >= 64) {
                     consume32<D, false>(st, v0, mcol, 32, prm.scale2, coef, rm, xm);
                     consume32<D, false>(st, v1, mcol + 32 * (kMetaFloats / 4), 32, prm.scale2, coef, rm, xm);
                 } else {
                     consume32<D, true>(st, v0, mcol, n_valid, prm.scale2, coef, rm, xm);
                     consume32<D, true>(st, v1, mcol + 32 * (kMetaFloats / 4), n_valid - 32, prm.scale2, coef, rm, xm);
                 }
-                mbar_arrive(&meta_empty[ms]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&meta_empty[ms]);
             }
             float* rec = prm.partials +
                          (static_cast<size_t>(blockIdx.x * dec.max_segs + it.seg) * 2 + half) * kPartFloats;

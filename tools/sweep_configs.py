@@ -21,7 +21,7 @@ from vosb200.sequence import lowres_dims  # noqa: E402
 K = 256
 
 
-def measure(H, W, n_obj, ref_num, topk, prec, frames=6, t0=46):
+def measure(H, W, n_obj, ref_num, topk, prec, frames=6, t0=46, probability=False):
     dev = torch.device('cuda', 0)
     T = t0 + frames
     H_d, W_d = lowres_dims(H, W)
@@ -37,17 +37,21 @@ def measure(H, W, n_obj, ref_num, topk, prec, frames=6, t0=46):
         f = proto[cm] + 0.1 * torch.randn(P, K, device=dev, generator=g)
         return f.t().reshape(K, H_d, W_d).to(feat_dtype).contiguous()
 
+    onehot = torch.zeros(n_obj + 1, P, device=dev).scatter_(0, cm.view(1, -1), 1.0)
     for t in range(t0 - 45, t0):                       # fill the ring's look-back window
         eng.append(t, feature(t))
-        eng.set_labels_index(t, cm.to(torch.uint8))
+        if probability:
+            eng.set_labels_dense(t, onehot)
+        else:
+            eng.set_labels_index(t, cm.to(torch.uint8))
     feats = [feature(t) for t in range(t0, T)]
     out = torch.empty((H, W), dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
     eng.enable_timing(8 * frames)
     for i, t in enumerate(range(t0, T)):
         eng.append(t, feats[i])
-        refs, sig = plan_refs(t, 40, ref_num, 8.0, 21.0, False)
-        eng.propagate(t, refs, sig, 1.0, False, want_prediction=False, want_lowres=False, want_fullres=False,
+        refs, sig = plan_refs(t, 40, ref_num, 8.0, 21.0, probability)
+        eng.propagate(t, refs, sig, 1.0, probability, want_prediction=False, want_lowres=False, want_fullres=False,
                       out_fullres=out, topk=topk)
     tm = eng.read_timing()
     eng.close()
@@ -55,12 +59,16 @@ def measure(H, W, n_obj, ref_num, topk, prec, frames=6, t0=46):
     total = sum(us.values())
     flops = 2.0 * P * (len(refs) * P) * K
     return {'H': H, 'W': W, 'pixels': P, 'objects': n_obj, 'ref_num': ref_num, 'refs_used': len(refs), 'topk': topk,
-            'precision': 'f16' if prec == PREC_F16 else 'split3', 'append_us': round(us['append'], 1),
+            'precision': 'f16' if prec == PREC_F16 else 'split3', 'probability_propagation': probability, 'append_us': round(us['append'], 1),
             'affinity_us': round(us['affinity'], 1), 'merge_us': round(us['merge'], 1),
             'frames_per_s_device': round(1e6 / total, 1), 'affinity_tflops_algorithmic': round(flops / us['affinity'] / 1e6, 1)}
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'prob':
+        for prec in (PREC_F16, PREC_SPLIT3):
+            print(json.dumps(dict(config='prob', **measure(480, 854, 2, 9, 0, prec, probability=True))), flush=True)
+        return
     for ref_num in (3, 5, 9, 12, 16, 20):
         for topk in (0, 5, 20, 50):
             print(json.dumps(dict(config=3, **measure(480, 854, 2, ref_num, topk, PREC_F16))), flush=True)
