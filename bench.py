@@ -161,6 +161,11 @@ def cpu_reference_sample(n_frames, steps, warmup):
     step; each frame = VOSNet.forward on CPU + predict + argmax/upsample.  fp32, all host threads."""
     from oracle import propagation_oracle as O
     from src.model.vos_net import VOSNet
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would make this a 1-thread run)
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, RuntimeError):
+        torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
     net = VOSNet('resnet50', pretrained=False).eval()
     t0_idx = 16
