@@ -1,5 +1,6 @@
 """`inference` command: same click surface and `inference_command_impl` signature as the
 reference's src/inference.py:18-113."""
+import os
 from pathlib import Path
 
 import click
@@ -63,7 +64,10 @@ def inference_command_impl(ref_num, data, resume, model, temperature, frame_rang
 
     dataset = InferenceDataset(str(Path(data) / 'JPEGImages/480p'), disable=disable,
                                inference_strategy=inference_strategy, scale=scale)
-    loader = torch.utils.data.DataLoader(dataset, batch_size=1, shuffle=False, num_workers=1, pin_memory=True)
+    # the reference decodes with one worker (inference.py:75-78); JPEG decode is the slowest stage once propagation runs on
+    # the GPU, so it is spread over workers here (same PIL decode, same order: shuffle=False)
+    loader = torch.utils.data.DataLoader(dataset, batch_size=1, shuffle=False, num_workers=min(8, os.cpu_count() or 1),
+                                         pin_memory=True, prefetch_factor=4, persistent_workers=False)
     annotation_dir = Path(data) / 'Annotations/480p'
     last_video = sorted(annotation_dir.glob('*'))[0].name
     common = (loader, len(dataset), annotation_dir, last_video, save, sigma_1, sigma_2, frame_range, ref_num,

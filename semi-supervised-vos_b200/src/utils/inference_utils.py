@@ -57,11 +57,58 @@ class _VideoSink:
         return self.chunks[-1][self.fill - 1]
 
     def flush(self):
+        """One D2H copy into pinned memory, then PNG encoding on a writer thread: the next video's propagation does
+        not wait for the files of this one (reference: save_predictions on the critical path, inference_utils.py:30)."""
         if not self.chunks:
             return
         parts = [c for c in self.chunks[:-1]] + [self.chunks[-1][:self.fill]]
-        masks = torch.cat(parts, 0).cpu().numpy()   # the only sync of the video
-        save_predictions(masks, self.palette, self.save, self.video)
+        dev_masks = torch.cat(parts, 0)
+        host = torch.empty(dev_masks.shape, dtype=torch.uint8, pin_memory=True)
+        host.copy_(dev_masks, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        _WRITER.submit(done, host, self.palette, self.save, self.video)
+
+
+class _PngWriter:
+    """Background writer of finished videos (bounded: at most two videos wait for their files)."""
+
+    def __init__(self):
+        self._queue, self._thread = None, None
+
+    def _run(self):
+        while True:
+            item = self._queue.get()
+            try:
+                if item is None:
+                    return
+                done, host, palette, save, video = item
+                done.synchronize()
+                save_predictions(host.numpy(), palette, save, video)
+            except BaseException as exc:  # noqa: BLE001 - surfaced by drain()
+                self._error = exc
+            finally:
+                self._queue.task_done()
+
+    def submit(self, *item):
+        import queue
+        import threading
+        if self._thread is None or not self._thread.is_alive():
+            self._queue, self._error = queue.Queue(maxsize=2), None
+            self._thread = threading.Thread(target=self._run, name='vos-png-writer', daemon=True)
+            self._thread.start()
+        self._queue.put(item)
+
+    def drain(self):
+        """Block until every submitted video is on disk; re-raise a writer failure."""
+        if self._queue is not None:
+            self._queue.join()
+            if self._error is not None:
+                err, self._error = self._error, None
+                raise err
+
+
+_WRITER = _PngWriter()
 
 
 def inference_single(model, inference_loader, total_len, annotation_dir, last_video, save, sigma_1, sigma_2,
@@ -102,6 +149,7 @@ def inference_single(model, inference_loader, total_len, annotation_dir, last_vi
         frame_idx += 1
     if sink is not None:
         sink.flush()
+    _WRITER.drain()          # every PNG of the run is on disk when the function returns, as in the reference
 
 
 # ------------------------------------------------------------------------------------------------
@@ -198,6 +246,7 @@ def _inference_two_streams(models, inference_loader, total_len, annotation_dir, 
         frame_idx += 1
     if sink is not None:
         sink.flush()
+    _WRITER.drain()
 
 
 def inference_hor_flip(model, inference_loader, total_len, annotation_dir, last_video, save, sigma_1, sigma_2,
