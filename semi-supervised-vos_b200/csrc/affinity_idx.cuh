@@ -460,7 +460,7 @@ __device__ __forceinline__ void chain_init(float a0, float b0, float gamma, floa
 // 16-column chains.  The first capture of the single-pass kernel showed every epilogue warp latency-bound on that
 // bookkeeping (~9 cycles per instruction, 4 warps per scheduler), not on MUFU or issue slots.
 // jw = first of the 32 columns that lies on the next image row (>= 32: none).
-template <int D>
+template <int D, bool kWide>
 __device__ __forceinline__ void fast_tile32(RowAcc<D>& st, float (&va)[kQC], float (&vb)[kQC], uint32_t cls_lane, uint32_t cls0,
                                             uint32_t same32, int dn, float bx, int jw, const PriorConst& pc, float inv_w,
                                             float scale2, float w_lowres) {
@@ -477,7 +477,35 @@ __device__ __forceinline__ void fast_tile32(RowAcc<D>& st, float (&va)[kQC], flo
     }
     const float drc = static_cast<float>(dn) * inv_w;
     float ta, tb, sa, sb;           // step sums (of v[]) and the factors still missing from them
-    if (jw >= 2 * kQC) {
+    bool direct = false;            // evaluate both halves directly (recurrence unsafe somewhere in the warp)
+    bool far_a = false, far_b = false;
+    if (kWide && !pc.chain_always) {
+        // Wide maps / narrow sigma (1080p with sigma = 8): the frame-level bound does not hold, so each tile tests its own
+        // two steps.  `far`: every weight of the step underflows fp32 (exp(-d^2/sigma^2) == 0 in the reference as well);
+        // unsafe: the exponent spread inside a step is too large for the recurrence and the step is not far.
+        float a0, b0;
+        quad_coeffs(drc, bx, inv_w, pc.coef, 0.f, a0, b0);
+        const float a1 = fmaf(16.f, b0, fmaf(256.f, pc.gamma, a0)), b1 = fmaf(32.f, pc.gamma, b0);
+        far_a = fmaf(-57.f, pc.gamma, fmaxf(a0, fmaf(15.f, b0, fmaf(225.f, pc.gamma, a0)))) < -150.f;
+        far_b = fmaf(-57.f, pc.gamma, fmaxf(a1, fmaf(15.f, b1, fmaf(225.f, pc.gamma, a1)))) < -150.f;
+        const bool ok_a = fmaf(fabsf(b0), 15.f, -225.f * pc.gamma) < 100.f, ok_b = fmaf(fabsf(b1), 15.f, -225.f * pc.gamma) < 100.f;
+        direct = jw < 2 * kQC || !__all_sync(full, (ok_a || far_a) && (ok_b || far_b));
+        if (!direct && __all_sync(full, far_a && far_b)) {
+            // nothing of this tile reaches the numerators: only the softmax denominator grows
+            const float neg_m = -st.m;
+            const float2 s2 = make_float2(scale2, scale2), nm2 = make_float2(neg_m, neg_m);
+            float2 l2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < kQC; j += 2) {
+                const float2 ea = ffma2(make_float2(va[j], va[j + 1]), s2, nm2);
+                const float2 eb = ffma2(make_float2(vb[j], vb[j + 1]), s2, nm2);
+                l2 = fadd2(l2, fadd2(make_float2(ex2(ea.x), ex2(ea.y)), make_float2(ex2(eb.x), ex2(eb.y))));
+            }
+            st.l += l2.x + l2.y;
+            return;
+        }
+    }
+    if (jw >= 2 * kQC && !direct) {
         const float neg_m = -st.m;
         const float2 s2 = make_float2(scale2, scale2);
         const float2 nm2 = make_float2(neg_m, neg_m);
@@ -488,6 +516,8 @@ __device__ __forceinline__ void fast_tile32(RowAcc<D>& st, float (&va)[kQC], flo
         float2 Ga, Ra, Gb, Rb;
         chain_init(a0, b0, pc.gamma, Ga, Ra, sa);
         chain_init(a1, b1, pc.gamma, Gb, Rb, sb);
+        if (kWide && far_a) { Ga = Ra = make_float2(0.f, 0.f); sa = 0.f; }
+        if (kWide && far_b) { Gb = Rb = make_float2(0.f, 0.f); sb = 0.f; }
         float2 l2 = make_float2(0.f, 0.f), suma = make_float2(0.f, 0.f), sumb = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < kQC; j += 2) {
@@ -515,15 +545,16 @@ __device__ __forceinline__ void fast_tile32(RowAcc<D>& st, float (&va)[kQC], flo
         // one image-row wrap inside the 32 columns: the half that contains it evaluates its exponents directly,
         // the other half runs its chain with the geometry of its own row
         float a0, b0;
-        if (jw < kQC) {
+        if (jw < kQC || (kWide && direct)) {
             sa = step16_direct<D>(st, va, drc, bx, jw, 0xffffu, pc, inv_w, scale2, w_lowres, ta);
         } else {
             quad_coeffs(drc, bx, inv_w, pc.coef, 0.f, a0, b0);
             sa = step16_chain<D>(st, va, a0, b0, fmaxf(a0, fmaf(15.f, b0, fmaf(225.f, pc.gamma, a0))), true, pc, scale2, ta);
         }
         const float drc_b = static_cast<float>(dn + kQC) * inv_w;
-        if (jw > kQC) {
-            sb = step16_direct<D>(st, vb, drc_b, bx + static_cast<float>(kQC), jw - kQC, 0xffffu, pc, inv_w, scale2, w_lowres, tb);
+        if (jw > kQC || (kWide && direct)) {
+            sb = step16_direct<D>(st, vb, drc_b, bx + static_cast<float>(kQC) - (jw <= kQC ? w_lowres : 0.f), jw > kQC ? jw - kQC : 2 * kQC,
+                                  0xffffu, pc, inv_w, scale2, w_lowres, tb);
         } else {
             quad_coeffs(drc_b, bx + static_cast<float>(kQC) - w_lowres, inv_w, pc.coef, 0.f, a0, b0);
             sb = step16_chain<D>(st, vb, a0, b0, fmaxf(a0, fmaf(15.f, b0, fmaf(225.f, pc.gamma, a0))), true, pc, scale2, tb);
@@ -546,7 +577,10 @@ __device__ __forceinline__ void fast_tile32(RowAcc<D>& st, float (&va)[kQC], flo
     }
 }
 
-template <int D, bool kSplit>
+// kWide: the frame-level bound that makes the prior recurrence safe everywhere (PriorConst::chain_always) fails for
+// some reference of this step (1080p with sigma = 8): tiles test themselves.  A separate instantiation, because the extra
+// live values cost the 96-register kernel 3.6 % at 480p.
+template <int D, bool kSplit, bool kWide>
 __global__ void __launch_bounds__(kIdxThreads, 1)   // 18 warps: 5 on two of the schedulers -> 16384 / (5 * 32) = 96 registers
 vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
                  const __grid_constant__ AffinityParams prm) {
@@ -608,7 +642,7 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                 const uint32_t taddr = pp.tmem_base + lane_base + buf * kTile + sub * 32;
                 const uint32_t cls0 = __shfl_sync(full, cls_lane, 0);
                 const uint32_t same32 = __ballot_sync(full, cls_lane == cls0);
-                if (valid32 == full && pc.chain_always && prm.dbg == 0) {
+                if (valid32 == full && (kWide || pc.chain_always) && prm.dbg == 0) {
                     float va[kQC], vb[kQC];
                     tmem_ld_32x32b_x16(taddr, va);
                     tmem_ld_32x32b_x16(taddr + kQC, vb);
@@ -616,7 +650,7 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_s(pp.acc_empty + 8 * buf);
-                    fast_tile32<D>(st, va, vb, cls_lane, cls0, same32, dn, static_cast<float>(x_sub - xm), W - x_sub, pc, inv_w, scale2, w_f);
+                    fast_tile32<D, kWide>(st, va, vb, cls_lane, cls0, same32, dn, static_cast<float>(x_sub - xm), W - x_sub, pc, inv_w, scale2, w_f);
                 } else {
                 int xq = x_sub;
 #pragma unroll 1

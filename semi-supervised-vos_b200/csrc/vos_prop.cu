@@ -137,12 +137,20 @@ int encode_maps(vosprop_engine* e) {
 
 template <int D>
 int launch_affinity(vosprop_engine* e, const vosk::AffinityParams& prm, int grid, int kernel, cudaStream_t st) {
-    if (kernel == VOSPROP_KERNEL_TC && prm.feat_fmt == vosk::kFmtSplit) {
-        VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_idx<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kIdxSmem));
-        VOS_CUDA(launch_pdl(vosk::vos_affinity_idx<D, true>, grid, vosk::kIdxThreads, vosk::kIdxSmem, st, e->tmap_hi, e->tmap_lo, prm));
-    } else if (kernel == VOSPROP_KERNEL_TC) {
-        VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_idx<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kIdxSmem));
-        VOS_CUDA(launch_pdl(vosk::vos_affinity_idx<D, false>, grid, vosk::kIdxThreads, vosk::kIdxSmem, st, e->tmap_hi, e->tmap_lo, prm));
+    if (kernel == VOSPROP_KERNEL_TC) {
+        // same bound as vosk::prior_const: is the prior recurrence safe for every reference of this step?
+        bool wide = false;
+        const float inv_w = prm.inv_w, w = static_cast<float>(prm.w_lowres), h = static_cast<float>((prm.n_pixels + prm.w_lowres - 1) / prm.w_lowres);
+        for (int r = 0; r < prm.n_refs; ++r) {
+            const float coef = prm.ref_coef[r], gamma = -coef * (inv_w * inv_w + 1.0f);
+            wide = wide || !(30.f * coef * (h * inv_w + w) - 225.f * gamma < 100.f);
+        }
+        const bool split = prm.feat_fmt == vosk::kFmtSplit;
+        void (*kern)(CUtensorMap, CUtensorMap, vosk::AffinityParams) =
+            split ? (wide ? vosk::vos_affinity_idx<D, true, true> : vosk::vos_affinity_idx<D, true, false>)
+                  : (wide ? vosk::vos_affinity_idx<D, false, true> : vosk::vos_affinity_idx<D, false, false>);
+        VOS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kIdxSmem));
+        VOS_CUDA(launch_pdl(kern, grid, vosk::kIdxThreads, vosk::kIdxSmem, st, e->tmap_hi, e->tmap_lo, prm));
     } else if (kernel == VOSPROP_KERNEL_TC_DENSE) {
         VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kSmemTc));
         vosk::vos_affinity_tc<D><<<grid, vosk::kTcThreads, vosk::kSmemTc, st>>>(e->tmap_hi, e->tmap_lo, prm);
