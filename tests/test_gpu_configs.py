@@ -139,3 +139,18 @@ def test_lanes_give_the_same_masks_as_one_sequence_at_a_time():
     for (feats, first, _), g in zip(clips, got):
         want = propagate_clip(_engine(20 * 40), feats, first)
         assert torch.equal(g, want)
+
+
+@pytest.mark.parametrize('size', [(40, 56), (264, 328)])
+def test_background_only_annotation(size):
+    """d = 1: the first annotation has no object (predict.py:113 gives d = max + 1 = 1); every frame must come out
+    background with probability mass equal to the prior-weighted softmax sum, as in the reference."""
+    from vosb200.sequence import propagate_clip
+    H, W = size
+    feats, _ = O.synthetic_sequence(5, H, W, 1, seed=91, feat_scale=0.30)
+    first = np.zeros((H, W), dtype=np.uint8)
+    eng = _engine(feats.shape[2] * feats.shape[3])
+    masks, preds = propagate_clip(eng, feats.cuda(), first, return_predictions=True)
+    want_masks, want_preds = O.propagate_sequence(feats, first)
+    assert preds.shape[1] == 1 and int(masks.max()) == 0 and int(want_masks.max()) == 0
+    assert float((preds.cpu() - torch.stack(want_preds)).abs().max()) <= PROB_ATOL
