@@ -19,14 +19,27 @@
 
 namespace vosk {
 
-constexpr int kTopkGroup = 2;                  // chunks per pipeline stage
-constexpr int kTopkStages = 3;                 // 3 x 32 KiB of reference chunks in flight
-constexpr int kTopkBuf = 112;                  // candidate slots per target pixel
-constexpr int kTopkMax = 64;                   // largest supported k  (kTopkBuf - 16 - kTopkMax >= 32 free slots after a prune)
-constexpr int kTopkEpiThreads = 128;
-constexpr int kTopkThreads = 64 + kTopkEpiThreads;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
-constexpr int kTopkSmem = kTopkStages * kTopkGroup * kChunkBytes + 512 + 1024 + kTopkBuf * kTile * 8;
-constexpr int kTopkMaxLists = 32;              // per-segment lists merged per target pixel (finish kernel)
+constexpr int kTopkGroup = 2;                  // chunks per pipeline stage (32 KiB)
+constexpr int kTopkMax = 64;                   // largest supported k
+constexpr int kTopkK16 = 8;                    // k <= this: 16 epilogue warps, 36 slots per thread
+constexpr int kTopkK8 = 24;                    // k <= this:  8 epilogue warps, 64 slots per thread; larger k: 4 warps, 112 slots
+constexpr int kTopkMaxCand = 2048;             // candidates merged per target pixel by the finish kernel (lists x k)
+
+// Shape of the top-k epilogue: kSub column groups per tile, 4 * kSub warps, one thread = one target pixel x 128 / kSub
+// columns with its own buffer.  kSub = 1: 112 slots (any k <= 64), one warp per scheduler -- latency bound
+// (profiles/README.md).  More warps hide that latency but shared memory caps the slots per thread (a buffer needs
+// k + 16 slots plus slack between prunes): kSub = 2: 64 slots (k <= 24), kSub = 4: 36 slots (k <= 8) -- at the price
+// of kSub lists per (CTA, segment, pixel) for the finish kernel to merge.
+template <int kSub>
+struct TopkCfg {
+    static constexpr int kEpiWarps = 4 * kSub;
+    static constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp 0 TMA, warp 1 MMA, then the epilogue warps
+    static constexpr int kBuf = kSub == 1 ? 112 : (kSub == 2 ? 64 : 36);   // candidate slots per thread
+    static constexpr int kStages = kSub == 1 ? 3 : 2;         // x 32 KiB of reference chunks in flight
+    static constexpr uint32_t kStride = 512u * kSub;          // bytes between consecutive slots of one thread
+    static constexpr int kCols = kTile / kSub;                // logit columns per thread and tile
+    static constexpr int kSmem = kStages * kTopkGroup * kChunkBytes + 512 + 1024 + kBuf * kTile * kSub * 8;
+};
 
 // order-preserving map float -> uint32 (larger float <=> larger key); -0.0 must be normalised to +0.0 by the caller
 __device__ __forceinline__ uint32_t f2key(float f) {
@@ -48,6 +61,7 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
 // Warp-synchronous prune of the 32 candidate buffers of a warp to their k best entries.
 // Buffer of a thread: slots e = 0..cnt-1 at kbase + 512*e (keys) / ibase + 512*e (indices), index-ascending.
 // Order: key descending, then index ascending (= slot order among equal keys).  tau <- the k-th best key.
+template <uint32_t kStride>
 __device__ __forceinline__ void topk_prune(uint32_t kbase, uint32_t ibase, int& cnt, int k, uint32_t& tau) {
     const uint32_t full = 0xffffffffu;
     const int cmax = __reduce_max_sync(full, cnt);
@@ -55,7 +69,7 @@ __device__ __forceinline__ void topk_prune(uint32_t kbase, uint32_t ibase, int& 
     uint32_t lo = 0xffffffffu, hi = 0u;
     for (int e = 0; e < cmax; ++e) {
         if (e < cnt) {
-            const uint32_t key = lds_u32(kbase + 512u * e);
+            const uint32_t key = lds_u32(kbase + kStride * e);
             lo = min(lo, key);
             hi = max(hi, key);
         }
@@ -67,7 +81,7 @@ __device__ __forceinline__ void topk_prune(uint32_t kbase, uint32_t ibase, int& 
         uint32_t mn = 0xffffffffu, mxb = 0u;                 // smallest key >= mid, largest key < mid
         for (int e = 0; e < cmax; ++e) {
             if (e < cnt) {
-                const uint32_t key = lds_u32(kbase + 512u * e);
+                const uint32_t key = lds_u32(kbase + kStride * e);
                 if (key >= mid) { ++c; mn = min(mn, key); }
                 else mxb = max(mxb, key);
             }
@@ -80,17 +94,17 @@ __device__ __forceinline__ void topk_prune(uint32_t kbase, uint32_t ibase, int& 
     if (!__any_sync(full, active)) return;
     int gt = 0;
     for (int e = 0; e < cmax; ++e)
-        if (active && e < cnt) gt += lds_u32(kbase + 512u * e) > lo;
+        if (active && e < cnt) gt += lds_u32(kbase + kStride * e) > lo;
     int need = k - gt, w = 0;                                // ties at the k-th key: the first `need` in slot order
     for (int e = 0; e < cmax; ++e) {
         if (active && e < cnt) {
-            const uint32_t key = lds_u32(kbase + 512u * e);
-            const uint32_t idx = lds_u32(ibase + 512u * e);
+            const uint32_t key = lds_u32(kbase + kStride * e);
+            const uint32_t idx = lds_u32(ibase + kStride * e);
             bool keep = key > lo;
             if (key == lo && need > 0) { keep = true; --need; }
             if (keep) {
-                sts_u32(kbase + 512u * w, key);
-                sts_u32(ibase + 512u * w, idx);
+                sts_u32(kbase + kStride * w, key);
+                sts_u32(ibase + kStride * w, idx);
                 ++w;
             }
         }
@@ -98,13 +112,16 @@ __device__ __forceinline__ void topk_prune(uint32_t kbase, uint32_t ibase, int& 
     if (active) { cnt = w; tau = lo; }
 }
 
-template <bool kSplit>
-__global__ void __launch_bounds__(kTopkThreads, 1)
+template <bool kSplit, int kSub>
+__global__ void __launch_bounds__(TopkCfg<kSub>::kThreads, 1)
 vos_affinity_topk(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
                   const __grid_constant__ AffinityParams prm) {
     using Cfg = IdxCfg<kSplit>;
+    using TC = TopkCfg<kSub>;
+    constexpr int kTopkStages = TC::kStages;
+    constexpr uint32_t kStride = TC::kStride;
     extern __shared__ uint8_t smem_raw[];
-    const IdxPipe pp = idx_setup<kTopkGroup, kTopkStages>(smem_raw, &tmap_hi, &tmap_lo, Cfg::kAccBufs, kTopkEpiThreads / 32);
+    const IdxPipe pp = idx_setup<kTopkGroup, kTopkStages>(smem_raw, &tmap_hi, &tmap_lo, Cfg::kAccBufs, TC::kEpiWarps);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const vosd::Decomp dec = vosd::make_decomp(prm.n_pixels, prm.n_refs, prm.num_sms);
@@ -114,38 +131,40 @@ vos_affinity_topk(const __grid_constant__ CUtensorMap tmap_hi, const __grid_cons
     } else if (warp == 1) {
         idx_role_mma<kSplit, kTopkGroup, kTopkStages>(pp, prm, dec);
     } else {
-        // ================= epilogue: warps 2-5; warp w owns TMEM lanes [32*(w%4), +32) = 32 target pixels
+        // ================= epilogue: warp w owns TMEM lanes [32*(w%4), +32) = 32 target pixels and the logit columns
+        // [kCols*sub, +kCols) of every tile
         const uint32_t full = 0xffffffffu;
         const int quarter = warp & 3;
+        const int sub = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
         const uint32_t buf_base = (pp.acc_empty + 8 * kIdxMaxAccBufs + 16 + 127) & ~127u;
-        const uint32_t kbase = buf_base + 4u * row;                          // keys    [kTopkBuf][128]
-        const uint32_t ibase = buf_base + kTopkBuf * kTile * 4 + 4u * row;   // indices [kTopkBuf][128]
+        const uint32_t kbase = buf_base + 4u * (sub * kTile + row);                                  // keys    [kBuf][128 * kSub]
+        const uint32_t ibase = buf_base + TC::kBuf * kTile * kSub * 4 + 4u * (sub * kTile + row);    // indices [kBuf][128 * kSub]
         const int k = prm.topk;
         const float temperature = prm.temperature;
         vosd::SegIter it(dec, blockIdx.x);
         int m_tile, n0, n1;
         uint32_t buf = 0, aphase = 0;
         while (it.next(m_tile, n0, n1)) {
-            idx_stage_target<kSplit>(pp, prm, it.seg, m_tile, row, lane_base, 0, 1);
+            idx_stage_target<kSplit>(pp, prm, it.seg, m_tile, row, lane_base, sub, kSub);
             int cnt = 0;
             uint32_t tau = 0u;                     // key of the running k-th best; 0 = below every real key
             float tau_f = -INFINITY;
             int r = n0 / dec.tpf;
             int j = n0 - r * dec.tpf;
             for (int nt = n0; nt < n1; ++nt) {
-                const int n_tile = r * prm.n_pixels + j * kTile;              // reference index (r*P + pixel) of column 0
-                const int cols = min(kTile, prm.n_pixels - j * kTile);        // real columns of this tile
+                const int n_tile = r * prm.n_pixels + j * kTile + sub * TC::kCols;   // reference index (r*P + pixel) of this thread's column 0
+                const int cols = min(kTile, prm.n_pixels - j * kTile) - sub * TC::kCols;  // its real columns in this tile
                 mbar_wait_s(pp.acc_full + 8 * buf, aphase);
                 tc_fence_after_sync();
-                const uint32_t taddr = pp.tmem_base + lane_base + buf * kTile;
+                const uint32_t taddr = pp.tmem_base + lane_base + buf * kTile + sub * TC::kCols;
 #pragma unroll 1
-                for (int s = 0; s < kTile / kQC; ++s) {
+                for (int s = 0; s < TC::kCols / kQC; ++s) {
                     float v[kQC];
                     tmem_ld_32x32b_x16(taddr + s * kQC, v);
                     tmem_ld_wait();
-                    if (s == kTile / kQC - 1) {                               // the whole tile row is in registers / consumed
+                    if (s == TC::kCols / kQC - 1) {                           // this thread's columns of the tile are consumed
                         tc_fence_before_sync();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_s(pp.acc_empty + 8 * buf);  // one arrival per warp
@@ -161,28 +180,28 @@ vos_affinity_topk(const __grid_constant__ CUtensorMap tmap_hi, const __grid_cons
 #pragma unroll
                     for (int i = 0; i < kQC; ++i) {
                         if (v[i] > tau_f) {
-                            sts_u32(kbase + 512u * cnt, f2key(v[i]));
-                            sts_u32(ibase + 512u * cnt, static_cast<uint32_t>(n_tile + s * kQC + i));
+                            sts_u32(kbase + kStride * cnt, f2key(v[i]));
+                            sts_u32(ibase + kStride * cnt, static_cast<uint32_t>(n_tile + s * kQC + i));
                             ++cnt;
                         }
                     }
-                    if (__any_sync(full, cnt > kTopkBuf - kQC)) {
-                        topk_prune(kbase, ibase, cnt, k, tau);
+                    if (__any_sync(full, cnt > TC::kBuf - kQC)) {
+                        topk_prune<kStride>(kbase, ibase, cnt, k, tau);
                         tau_f = tau ? key2f(tau) : -INFINITY;
                     }
                 }
                 if (++buf == Cfg::kAccBufs) { buf = 0; aphase ^= 1; }
                 if (++j == dec.tpf) { j = 0; ++r; }
             }
-            topk_prune(kbase, ibase, cnt, k, tau);
-            // ---- this segment's list of the target pixel: cnt <= k entries, index-ascending
-            const size_t rec = static_cast<size_t>(blockIdx.x * dec.max_segs + it.seg) * kTile + row;
+            topk_prune<kStride>(kbase, ibase, cnt, k, tau);
+            // ---- this thread's list of the target pixel for this segment: cnt <= k entries, index-ascending
+            const size_t rec = (static_cast<size_t>(blockIdx.x * dec.max_segs + it.seg) * kSub + sub) * kTile + row;
             prm.cand_cnt[rec] = cnt;
             uint32_t* ck = prm.cand_key + rec * kTopkMax;
             int32_t* ci = prm.cand_idx + rec * kTopkMax;
             for (int e = 0; e < cnt; ++e) {
-                ck[e] = lds_u32(kbase + 512u * e);
-                ci[e] = static_cast<int32_t>(lds_u32(ibase + 512u * e));
+                ck[e] = lds_u32(kbase + kStride * e);
+                ci[e] = static_cast<int32_t>(lds_u32(ibase + kStride * e));
             }
         }
     }
@@ -204,7 +223,7 @@ struct TopkFinishParams {
 };
 
 constexpr int kFinishWarps = 4;
-constexpr int kFinishSmem = kFinishWarps * (kTopkMaxLists * kTopkMax * 8 + kTopkMax * 8);
+constexpr int kFinishSmem = kFinishWarps * (kTopkMaxCand * 8 + kTopkMax * 8);
 
 __global__ void __launch_bounds__(kFinishWarps * 32) vos_topk_finish(const TopkFinishParams fp) {
     extern __shared__ uint32_t fsm[];
@@ -213,26 +232,28 @@ __global__ void __launch_bounds__(kFinishWarps * 32) vos_topk_finish(const TopkF
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pix = blockIdx.x * kFinishWarps + warp;
     if (pix >= prm.n_pixels) return;
-    uint32_t* keys = fsm + warp * (kTopkMaxLists * kTopkMax * 2 + kTopkMax * 2);   // [C]
-    uint32_t* idxs = keys + kTopkMaxLists * kTopkMax;                               // [C]
-    uint32_t* skey = idxs + kTopkMaxLists * kTopkMax;                               // [k] selected
+    uint32_t* keys = fsm + warp * (kTopkMaxCand * 2 + kTopkMax * 2);   // [C]
+    uint32_t* idxs = keys + kTopkMaxCand;                               // [C]
+    uint32_t* skey = idxs + kTopkMaxCand;                               // [k] selected
     uint32_t* sidx = skey + kTopkMax;
     const vosd::Decomp dec = vosd::make_decomp(prm.n_pixels, prm.n_refs, prm.num_sms);
     const int k = fp.topk;
     const int mt = pix / kTile, row = pix % kTile;
     const int64_t lin_lo = static_cast<int64_t>(mt) * dec.nt;
     const int c_first = vosd::cta_of(dec, lin_lo), c_last = vosd::cta_of(dec, lin_lo + dec.nt - 1);
-    // ---- gather the per-segment lists in CTA order: reference-index ranges ascend, so the list is index-ascending
+    // ---- gather the lists of every (CTA, segment, column group) that saw this pixel's row
     int C = 0;
     for (int c = c_first; c <= c_last; ++c) {
         const int seg = mt - static_cast<int>(vosd::cta_begin(dec, c) / dec.nt);
-        const size_t rec = static_cast<size_t>(c * dec.max_segs + seg) * kTile + row;
-        const int n = fp.cand_cnt[rec];
-        for (int e = lane; e < n; e += 32) {
-            keys[C + e] = fp.cand_key[rec * kTopkMax + e];
-            idxs[C + e] = static_cast<uint32_t>(fp.cand_idx[rec * kTopkMax + e]);
+        for (int sub = 0; sub < prm.n_sub; ++sub) {
+            const size_t rec = (static_cast<size_t>(c * dec.max_segs + seg) * prm.n_sub + sub) * kTile + row;
+            const int n = fp.cand_cnt[rec];
+            for (int e = lane; e < n; e += 32) {
+                keys[C + e] = fp.cand_key[rec * kTopkMax + e];
+                idxs[C + e] = static_cast<uint32_t>(fp.cand_idx[rec * kTopkMax + e]);
+            }
+            C += n;
         }
-        C += n;
     }
     __syncwarp();
     // ---- k-th best key by bisection over the keys (warp-cooperative counts)
@@ -258,20 +279,35 @@ __global__ void __launch_bounds__(kFinishWarps * 32) vos_topk_finish(const TopkF
         int gt = 0;
         for (int e = lane; e < C; e += 32) gt += keys[e] > lo;
         gt = __reduce_add_sync(full, gt);
-        int need = k - gt, w = 0;                 // ties at the k-th key: lowest reference index first = list order
+        // ties at the k-th key: the `need` lowest reference indices among them (the lists interleave column groups, so
+        // list order is not index order): largest index still kept = the need-th smallest tie index, by bisection
+        const int need = k - gt;
+        int n_tie = 0;
+        for (int e = lane; e < C; e += 32) n_tie += keys[e] == lo;
+        n_tie = __reduce_add_sync(full, n_tie);
+        uint32_t idx_cut = 0xffffffffu;
+        if (n_tie > need) {
+            uint32_t ilo = 0u, ihi = 0xffffffffu;               // smallest cut with #{tie, idx <= cut} >= need
+            while (ilo < ihi) {
+                const uint32_t mid = ilo + ((ihi - ilo) >> 1);
+                int c = 0;
+                for (int e = lane; e < C; e += 32) c += keys[e] == lo && idxs[e] <= mid;
+                c = __reduce_add_sync(full, c);
+                if (c >= need) ihi = mid; else ilo = mid + 1u;
+            }
+            idx_cut = ilo;
+        }
+        int w = 0;
         for (int e0 = 0; e0 < C; e0 += 32) {
             const int e = e0 + lane;
             const uint32_t key = e < C ? keys[e] : 0u;
-            const bool tie = e < C && key == lo;
-            const uint32_t tmask = __ballot_sync(full, tie);
-            const bool keep = e < C && (key > lo || (tie && __popc(tmask & ((1u << lane) - 1u)) < need));
+            const bool keep = e < C && (key > lo || (key == lo && idxs[e] <= idx_cut));
             const uint32_t kmask = __ballot_sync(full, keep);
             if (keep) {
                 const int pos = w + __popc(kmask & ((1u << lane) - 1u));
                 skey[pos] = key;
                 sidx[pos] = idxs[e];
             }
-            need -= min(need, __popc(tmask));
             w += __popc(kmask);
         }
         n_sel = w;
@@ -279,7 +315,7 @@ __global__ void __launch_bounds__(kFinishWarps * 32) vos_topk_finish(const TopkF
         for (int e = lane; e < C; e += 32) { skey[e] = keys[e]; sidx[e] = idxs[e]; }
     }
     __syncwarp();
-    // ---- order for the index output: value descending, reference index ascending (selected list is index-ascending)
+    // ---- order for the index output: value descending, reference index ascending
     if (fp.out_topk_idx) {
         for (int i = lane; i < k; i += 32) {
             if (i >= n_sel) fp.out_topk_idx[static_cast<size_t>(pix) * k + i] = -1;
@@ -287,7 +323,8 @@ __global__ void __launch_bounds__(kFinishWarps * 32) vos_topk_finish(const TopkF
         for (int i = lane; i < n_sel; i += 32) {
             const uint32_t ki = skey[i];
             int rank = 0;
-            for (int jj = 0; jj < n_sel; ++jj) rank += (skey[jj] > ki) || (skey[jj] == ki && jj < i);
+            const uint32_t ii = sidx[i];
+            for (int jj = 0; jj < n_sel; ++jj) rank += (skey[jj] > ki) || (skey[jj] == ki && sidx[jj] < ii);
             fp.out_topk_idx[static_cast<size_t>(pix) * k + rank] = static_cast<int32_t>(sidx[i]);
         }
     }

@@ -193,11 +193,15 @@ int propagate_topk(vosprop_engine* e, const vosprop_step* s, vosk::AffinityParam
     const vosd::Decomp dec = vosd::make_decomp(e->P, s->n_refs, grid_cap);
     const int64_t per_cta = dec.total / dec.grid;
     const int64_t lists = (dec.nt + per_cta - 1) / per_cta + 1;
-    if (lists > vosk::kTopkMaxLists)
-        return fail(VOSPROP_ERR_UNSUPPORTED, "top-k: %lld partial lists per target pixel (max %d)", (long long)lists, vosk::kTopkMaxLists);
+    // small k: more epilogue warps with smaller per-thread buffers (n_sub lists per CTA and segment)
+    int n_sub = s->topk <= vosk::kTopkK16 ? 4 : (s->topk <= vosk::kTopkK8 ? 2 : 1);
+    while (n_sub > 1 && lists * n_sub * s->topk > vosk::kTopkMaxCand) n_sub >>= 1;
+    if (lists * n_sub * s->topk > vosk::kTopkMaxCand)
+        return fail(VOSPROP_ERR_UNSUPPORTED, "top-k: %lld lists x k=%d candidates per target pixel (max %d)", (long long)(lists * n_sub),
+                    s->topk, vosk::kTopkMaxCand);
     ap.num_sms = grid_cap;
     if (!e->cand_key) {
-        const size_t rows = e->partial_records / vosk::kIdxSub * vosk::kTile;
+        const size_t rows = e->partial_records * vosk::kTile;     // partial_records counts 4 column groups per (CTA, segment)
         cudaError_t a1 = cudaMalloc(&e->cand_key, rows * vosk::kTopkMax * 4);
         cudaError_t a2 = cudaMalloc(&e->cand_idx, rows * vosk::kTopkMax * 4);
         cudaError_t a3 = cudaMalloc(&e->cand_cnt, rows * 4);
@@ -210,13 +214,15 @@ int propagate_topk(vosprop_engine* e, const vosprop_step* s, vosk::AffinityParam
     ap.cand_key = e->cand_key; ap.cand_idx = e->cand_idx; ap.cand_cnt = e->cand_cnt;
     {
         TimedLaunch timed(e, VOSPROP_T_AFFINITY, st);
-        if (ap.feat_fmt == vosk::kFmtSplit) {
-            VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_topk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kTopkSmem));
-            vosk::vos_affinity_topk<true><<<dec.grid, vosk::kTopkThreads, vosk::kTopkSmem, st>>>(e->tmap_hi, e->tmap_lo, ap);
-        } else {
-            VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_topk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kTopkSmem));
-            vosk::vos_affinity_topk<false><<<dec.grid, vosk::kTopkThreads, vosk::kTopkSmem, st>>>(e->tmap_hi, e->tmap_lo, ap);
-        }
+        const bool split = ap.feat_fmt == vosk::kFmtSplit;
+        void (*kern)(CUtensorMap, CUtensorMap, vosk::AffinityParams) =
+            n_sub == 4 ? (split ? vosk::vos_affinity_topk<true, 4> : vosk::vos_affinity_topk<false, 4>)
+          : n_sub == 2 ? (split ? vosk::vos_affinity_topk<true, 2> : vosk::vos_affinity_topk<false, 2>)
+                       : (split ? vosk::vos_affinity_topk<true, 1> : vosk::vos_affinity_topk<false, 1>);
+        const int smem = n_sub == 4 ? vosk::TopkCfg<4>::kSmem : (n_sub == 2 ? vosk::TopkCfg<2>::kSmem : vosk::TopkCfg<1>::kSmem);
+        const int threads = n_sub == 4 ? vosk::TopkCfg<4>::kThreads : (n_sub == 2 ? vosk::TopkCfg<2>::kThreads : vosk::TopkCfg<1>::kThreads);
+        VOS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<dec.grid, threads, smem, st>>>(e->tmap_hi, e->tmap_lo, ap);
         VOS_CUDA(cudaGetLastError());
     }
     if (s->record_event) VOS_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->record_event), st));
@@ -225,7 +231,7 @@ int propagate_topk(vosprop_engine* e, const vosprop_step* s, vosk::AffinityParam
     const int q_slot = ap.q_slot;
     mp.n_pixels = e->P; mp.p_pad = e->p_pad; mp.w_lowres = e->W_d; mp.h_lowres = e->H_d; mp.n_refs = s->n_refs;
     mp.num_sms = grid_cap; mp.d = e->d; mp.H = e->H; mp.W = e->W; mp.q_slot = q_slot;
-    mp.write_labels = s->write_labels; mp.probability = s->probability_propagation; mp.n_sub = 1;
+    mp.write_labels = s->write_labels; mp.probability = s->probability_propagation; mp.n_sub = n_sub;
     mp.partials = nullptr; mp.meta = e->meta; mp.cls = e->cls;
     mp.out_prediction = s->out_prediction;
     mp.out_mask_lowres = s->out_mask_lowres ? s->out_mask_lowres : (s->out_mask_fullres ? e->low_scratch : nullptr);
