@@ -59,24 +59,29 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
 }
 
 // Warp-synchronous prune of the 32 candidate buffers of a warp to their k best entries.
-// Buffer of a thread: slots e = 0..cnt-1 at kbase + 512*e (keys) / ibase + 512*e (indices), index-ascending.
+// Buffer of a thread: slots e = 0..cnt-1 at kbase + kStride*e (keys) / ibase + kStride*e (indices), index-ascending.
 // Order: key descending, then index ascending (= slot order among equal keys).  tau <- the k-th best key.
+// On entry tau is a lower bound of every key in the buffer (the k-th best of the last prune, or the key of -inf) and
+// kmax the largest key ever pushed, so no pass is needed to find the search interval; pivots alternate between
+// interpolation on the counts and plain bisection, and the bounds snap to actual keys after every pass (typically 4-6
+// passes over the buffer instead of ~14 with min/max + pure bisection + a separate count).
 template <uint32_t kStride>
-__device__ __forceinline__ void topk_prune(uint32_t kbase, uint32_t ibase, int& cnt, int k, uint32_t& tau) {
+__device__ __forceinline__ void topk_prune(uint32_t kbase, uint32_t ibase, int& cnt, int k, uint32_t& tau, uint32_t kmax) {
     const uint32_t full = 0xffffffffu;
     const int cmax = __reduce_max_sync(full, cnt);
     const bool active = cnt > k;
-    uint32_t lo = 0xffffffffu, hi = 0u;
-    for (int e = 0; e < cmax; ++e) {
-        if (e < cnt) {
-            const uint32_t key = lds_u32(kbase + kStride * e);
-            lo = min(lo, key);
-            hi = max(hi, key);
-        }
-    }
-    // f(t) = #{key >= t}.  Invariant: f(lo) >= k, f(hi + 1) < k, lo and hi are keys of the buffer.
+    // f(t) = #{key >= t}.  Invariant: f(lo) >= k (cge = f(lo)), #{key > hi} < k (cgt), hi is a key.
+    uint32_t lo = tau, hi = kmax;
+    int cge = cnt, cgt = 0;
+    bool interp = true;
     while (__any_sync(full, active && lo < hi)) {
-        const uint32_t mid = lo + ((hi - lo) >> 1) + 1u;    // lo < mid <= hi
+        uint32_t mid = lo + ((hi - lo) >> 1) + 1u;           // lo < mid <= hi
+        if (interp) {   // keys roughly uniform in (lo, hi]: the k-th best sits (cge - k) / (cge - cgt) of the way up
+            const float t = (static_cast<float>(cge - k) + 0.5f) / static_cast<float>(cge - cgt);
+            const uint32_t off = static_cast<uint32_t>(t * static_cast<float>(hi - lo));
+            mid = lo + min(max(off, 1u), hi - lo);
+        }
+        interp = !interp;
         int c = 0;
         uint32_t mn = 0xffffffffu, mxb = 0u;                 // smallest key >= mid, largest key < mid
         for (int e = 0; e < cmax; ++e) {
@@ -87,15 +92,12 @@ __device__ __forceinline__ void topk_prune(uint32_t kbase, uint32_t ibase, int& 
             }
         }
         if (active && lo < hi) {
-            if (c >= k) lo = mn;
-            else hi = mxb;
+            if (c >= k) { lo = mn; cge = c; }
+            else { hi = mxb; cgt = c; }
         }
     }
     if (!__any_sync(full, active)) return;
-    int gt = 0;
-    for (int e = 0; e < cmax; ++e)
-        if (active && e < cnt) gt += lds_u32(kbase + kStride * e) > lo;
-    int need = k - gt, w = 0;                                // ties at the k-th key: the first `need` in slot order
+    int need = k - cgt, w = 0;                               // ties at the k-th key: the first `need` in slot order
     for (int e = 0; e < cmax; ++e) {
         if (active && e < cnt) {
             const uint32_t key = lds_u32(kbase + kStride * e);
@@ -146,10 +148,12 @@ vos_affinity_topk(const __grid_constant__ CUtensorMap tmap_hi, const __grid_cons
         vosd::SegIter it(dec, blockIdx.x);
         int m_tile, n0, n1;
         uint32_t buf = 0, aphase = 0;
+        long long n_steps = 0, n_slow = 0, n_push = 0, n_prune = 0;     // profiling counters (vosprop_debug_clocks)
         while (it.next(m_tile, n0, n1)) {
             idx_stage_target<kSplit>(pp, prm, it.seg, m_tile, row, lane_base, sub, kSub);
             int cnt = 0;
-            uint32_t tau = 0u;                     // key of the running k-th best; 0 = below every real key
+            uint32_t tau = f2key(-INFINITY);       // key of the running k-th best (a lower bound of every buffered key)
+            uint32_t kmax = 0u;                    // largest key pushed in this segment
             float tau_f = -INFINITY;
             int r = n0 / dec.tpf;
             int j = n0 - r * dec.tpf;
@@ -171,29 +175,35 @@ vos_affinity_topk(const __grid_constant__ CUtensorMap tmap_hi, const __grid_cons
                     }
                     const int nv = cols - s * kQC;
                     if (nv <= 0) continue;
+                    ++n_steps;
 #pragma unroll
                     for (int i = 0; i < kQC; ++i) {
                         v[i] = v[i] * temperature + 0.0f;                     // predict.py:52 (fp32 product); -0 -> +0
                         if (i >= nv) v[i] = -INFINITY;
                     }
                     if (!__any_sync(full, max16(v) > tau_f)) continue;        // nothing beats any lane's k-th best
+                    ++n_slow;
 #pragma unroll
                     for (int i = 0; i < kQC; ++i) {
                         if (v[i] > tau_f) {
-                            sts_u32(kbase + kStride * cnt, f2key(v[i]));
+                            const uint32_t key = f2key(v[i]);
+                            kmax = max(kmax, key);
+                            ++n_push;
+                            sts_u32(kbase + kStride * cnt, key);
                             sts_u32(ibase + kStride * cnt, static_cast<uint32_t>(n_tile + s * kQC + i));
                             ++cnt;
                         }
                     }
                     if (__any_sync(full, cnt > TC::kBuf - kQC)) {
-                        topk_prune<kStride>(kbase, ibase, cnt, k, tau);
-                        tau_f = tau ? key2f(tau) : -INFINITY;
+                        ++n_prune;
+                        topk_prune<kStride>(kbase, ibase, cnt, k, tau, kmax);
+                        tau_f = key2f(tau);
                     }
                 }
                 if (++buf == Cfg::kAccBufs) { buf = 0; aphase ^= 1; }
                 if (++j == dec.tpf) { j = 0; ++r; }
             }
-            topk_prune<kStride>(kbase, ibase, cnt, k, tau);
+            topk_prune<kStride>(kbase, ibase, cnt, k, tau, kmax);
             // ---- this thread's list of the target pixel for this segment: cnt <= k entries, index-ascending
             const size_t rec = (static_cast<size_t>(blockIdx.x * dec.max_segs + it.seg) * kSub + sub) * kTile + row;
             prm.cand_cnt[rec] = cnt;
@@ -203,6 +213,12 @@ vos_affinity_topk(const __grid_constant__ CUtensorMap tmap_hi, const __grid_cons
                 ck[e] = lds_u32(kbase + kStride * e);
                 ci[e] = static_cast<int32_t>(lds_u32(ibase + kStride * e));
             }
+        }
+        if (prm.dbg_clk && warp == 2 && lane == 0) {
+            prm.dbg_clk[blockIdx.x * 16 + 9] = n_steps;
+            prm.dbg_clk[blockIdx.x * 16 + 10] = n_slow;
+            prm.dbg_clk[blockIdx.x * 16 + 11] = n_push;
+            prm.dbg_clk[blockIdx.x * 16 + 12] = n_prune;
         }
     }
     idx_teardown(pp);
