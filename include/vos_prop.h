@@ -21,7 +21,9 @@ extern "C" {
 
 #define VOSPROP_ABI_VERSION 3
 #define VOSPROP_MAX_REFS 32     /* reference frames per step (reference default ref_num = 9)   */
-#define VOSPROP_MAX_CLASSES 14  /* d = objects + 1 (DAVIS <= 11, YouTube-VOS <= 11)            */
+#define VOSPROP_MAX_CLASSES 24  /* d = objects + 1; 15..24 (validation: 22 annotation centroids, src/train.py:206) run with index
+                                   labels only: no dense labels, no probability propagation, no top-k, W_d >= 32   */
+#define VOSPROP_MAX_DENSE_CLASSES 14  /* DAVIS <= 11, YouTube-VOS <= 11: every label kind and kernel                 */
 #define VOSPROP_FEAT_DIM 256    /* VOSNet embedding width, src/model/vos_net.py:22             */
 #define VOSPROP_TILE 128        /* pixel tile of the affinity kernel                           */
 #define VOSPROP_MAX_TOPK 64     /* largest k of the top-k extension                            */

@@ -10,6 +10,8 @@ are applied to the *environment*, never to the reference's sources:
   1. ``numpy.int``            (src/model/predict.py:85, src/utils/datasets.py:145)
   2. ``PIL.Image.ANTIALIAS``  (src/utils/datasets.py:146)
   3. ``model_zoo.load_url``   (src/model/backbone/resnet.py:194 -- pretrained download, no network)
+  4. ``skimage.morphology``   (src/model/triplet_miners.py:15 -- not installed here; only the skeleton miners call it,
+                               the validation golden uses CrossEntropy) -- see import_validation()
 """
 from __future__ import annotations
 
@@ -61,6 +63,30 @@ def import_reference(device: str = 'cpu'):
         ns.resnet = resnet
     finally:
         sys.path.remove(str(root))
+    return ns
+
+
+def import_validation(ns):
+    """Adds the reference's loss / train / datasets modules (validation path) to `ns`."""
+    import types
+    if 'skimage' not in sys.modules:
+        try:
+            importlib.import_module('skimage.morphology')
+        except ImportError:   # shim 4
+            sk, mo = types.ModuleType('skimage'), types.ModuleType('skimage.morphology')
+
+            def skeletonize(*a, **k):
+                raise RuntimeError('skimage is not installed: the skeleton miners cannot run in this container')
+            mo.skeletonize = skeletonize
+            sk.morphology = mo
+            sys.modules['skimage'], sys.modules['skimage.morphology'] = sk, mo
+    sys.path.insert(0, str(ns.root))
+    try:
+        ns.loss = importlib.import_module('src.model.loss')
+        ns.train = importlib.import_module('src.train')
+        ns.datasets = importlib.import_module('src.utils.datasets')
+    finally:
+        sys.path.remove(str(ns.root))
     return ns
 
 

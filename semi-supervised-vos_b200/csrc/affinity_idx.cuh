@@ -421,27 +421,26 @@ __device__ __forceinline__ float step16_direct(RowAcc<D>& st, float (&v)[kQC], f
 }
 
 // Label gather of a class-mixed step: v[] holds the 16 weights (times `scale`), `cls_lane` the class byte of the warp's
-// column `lane` (this step: lanes [lane_shift, +16)), `mk` the columns of class `c` (both warp-uniform).  One pass per
-// class present; the last class receives the remainder of the step total.
+// column `lane` (this step: lanes [lane_shift, +16)), `mk` the columns of class `c` (both warp-uniform).  One masked sum
+// per class present -- no class takes "the step total minus the others": that cancellation would leave an absolute error
+// of ~1e-7 x total in a class whose own weights are tiny, which the validation loss (log of the true class's probability,
+// loss.py:60) would see.
 template <int D>
 __device__ __forceinline__ void gather_mixed(RowAcc<D>& st, const float (&v)[kQC], uint32_t cls_lane, int lane_shift,
-                                             uint32_t valid, uint32_t c, uint32_t mk, float sum, float scale) {
+                                             uint32_t valid, uint32_t c, uint32_t mk, float /*sum*/, float scale) {
     const uint32_t full = 0xffffffffu;
     uint32_t rem = valid;
-    float rest = sum;
     while (true) {
-        rem &= ~mk;
-        if (rem == 0u) break;
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < kQC; ++j)
             if ((mk >> j) & 1u) s += v[j];
         add_to_class<D>(st, static_cast<int>(c), s * scale);
-        rest -= s;
+        rem &= ~mk;
+        if (rem == 0u) break;
         c = __shfl_sync(full, cls_lane, lane_shift + __ffs(rem) - 1);
         mk = (__ballot_sync(full, cls_lane == c) >> lane_shift) & rem;
     }
-    add_to_class<D>(st, static_cast<int>(c), fmaxf(rest, 0.f) * scale);
 }
 
 // Chain initialisation of one 16-column step (see step16_chain): G, Rho and the factor 2^sh still missing from the sums.

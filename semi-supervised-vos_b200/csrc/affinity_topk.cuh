@@ -352,9 +352,9 @@ __global__ void __launch_bounds__(kFinishWarps * 32) vos_topk_finish(const TopkF
     tmax = fmaxf(tmax, __shfl_xor_sync(full, tmax, 4));
     tmax = fmaxf(tmax, __shfl_xor_sync(full, tmax, 2));
     tmax = fmaxf(tmax, __shfl_xor_sync(full, tmax, 1));
-    float L = 0.f, acc[kMaxClasses];
+    float L = 0.f, acc[kMetaClasses];
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c) acc[c] = 0.f;
+    for (int c = 0; c < kMetaClasses; ++c) acc[c] = 0.f;
     float rm, xm;
     pixel_coord(pix, prm.w_lowres, rm, xm);
     for (int i = lane; i < n_sel; i += 32) {
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(kFinishWarps * 32) vos_topk_finish(const TopkF
     for (int off = 16; off > 0; off >>= 1) {
         L += __shfl_xor_sync(full, L, off);
 #pragma unroll
-        for (int c = 0; c < kMaxClasses; ++c) acc[c] += __shfl_xor_sync(full, acc[c], off);
+        for (int c = 0; c < kMetaClasses; ++c) acc[c] += __shfl_xor_sync(full, acc[c], off);
     }
     if (lane != 0) return;
     const float inv = 1.0f / L;
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(kFinishWarps * 32) vos_topk_finish(const TopkF
     float best_v = -INFINITY;
     float* mrec = prm.meta + (static_cast<size_t>(prm.q_slot) * prm.p_pad + pix) * kMetaFloats + 2;
 #pragma unroll
-    for (int c = 0; c < kMaxClasses; ++c) {
+    for (int c = 0; c < kMetaClasses; ++c) {
         if (c < prm.d) {
             const float pk = acc[c] * inv;
             acc[c] = pk;
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(kFinishWarps * 32) vos_topk_finish(const TopkF
     }
     if (prm.write_labels) {
 #pragma unroll
-        for (int c = 0; c < kMaxClasses; ++c)
+        for (int c = 0; c < kMetaClasses; ++c)
             mrec[c] = (c < prm.d) ? (prm.probability ? acc[c] : (c == best ? 1.f : 0.f)) : 0.f;
         prm.cls[static_cast<size_t>(prm.q_slot) * prm.p_pad + pix] = static_cast<uint8_t>(best);
     }

@@ -39,8 +39,9 @@ constexpr int kAccBufs = 4;          // TMEM accumulator ring: 4 x 128 columns =
 constexpr int kTcThreads = 384;      // warp 0 TMA, 1 MMA, 2 meta, 3 idle, 4-11 epilogue
 constexpr int kEpiThreads = 256;
 constexpr int kSmemTc = kQBytes + kStages * kChunkBytes + kMetaStages * kMetaTileBytes + 512 + 1024;
-constexpr int kMaxClasses = 14;
-constexpr int kPartFloats = (2 + kMaxClasses) * kTile;  // one partial record: m, l, acc[14] x 128 rows
+constexpr int kMetaClasses = 14;      // label floats a meta record holds (dense / top-k / probability paths)
+constexpr int kMaxClasses = 24;       // index-label path only: class bytes, no meta record needed (validation, d = 22)
+constexpr int kPartFloats = (2 + kMaxClasses) * kTile;  // one partial record: m, l, acc[<= 24] x 128 rows
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kNegBig = -1.0e30f;  // finite "minus infinity" for the running max
 
@@ -511,6 +512,7 @@ __global__ void vos_decomp_tables(int32_t* __restrict__ tab, int n_pixels, int n
 constexpr int kMergeThreads = 1024;   // 128 pixel groups of 8 lanes
 constexpr int kMergeLanes = 8;        // lanes cooperating on one target pixel
 
+template <int kCap>   // class capacity of this instantiation: kMetaClasses (the product path) or kCap
 __global__ void __launch_bounds__(kMergeThreads) vos_merge_writeback(const MergeParams prm) {
     extern __shared__ uint8_t row_cls[];  // [w_lowres]
     pdl_launch_dependents();
@@ -525,9 +527,9 @@ __global__ void __launch_bounds__(kMergeThreads) vos_merge_writeback(const Merge
         const int c_first = prm.tables[mt], c_last = prm.tables[prm.tpf + mt];
         const int n_rec = (c_last - c_first + 1) * prm.n_sub;
         // each lane folds records sublane, sublane+8, ... (online softmax merge), then an 8-lane butterfly
-        float M = kNegBig, L = 0.f, acc[kMaxClasses];
+        float M = kNegBig, L = 0.f, acc[kCap];
 #pragma unroll
-        for (int k = 0; k < kMaxClasses; ++k) acc[k] = 0.f;
+        for (int k = 0; k < kCap; ++k) acc[k] = 0.f;
         for (int i = sublane; i < n_rec; i += kMergeLanes) {
             const int c = c_first + i / prm.n_sub, h = i % prm.n_sub;
             const int seg = mt - mt0[c];
@@ -537,7 +539,7 @@ __global__ void __launch_bounds__(kMergeThreads) vos_merge_writeback(const Merge
             const float w_old = vosptx::ex2(M - M_new), w_new = vosptx::ex2(m_r - M_new);
             L = fmaf(rec[kTile + row], w_new, L * w_old);
 #pragma unroll
-            for (int k = 0; k < kMaxClasses; ++k)
+            for (int k = 0; k < kCap; ++k)
                 if (k < prm.d) acc[k] = fmaf(rec[(2 + k) * kTile + row], w_new, acc[k] * w_old);
             M = M_new;
         }
@@ -548,7 +550,7 @@ __global__ void __launch_bounds__(kMergeThreads) vos_merge_writeback(const Merge
             const float w_a = vosptx::ex2(M - M_new), w_b = vosptx::ex2(M_o - M_new);
             L = fmaf(__shfl_xor_sync(gmask, L, off), w_b, L * w_a);
 #pragma unroll
-            for (int k = 0; k < kMaxClasses; ++k)
+            for (int k = 0; k < kCap; ++k)
                 if (k < prm.d) acc[k] = fmaf(__shfl_xor_sync(gmask, acc[k], off), w_b, acc[k] * w_a);
             M = M_new;
         }
@@ -558,7 +560,7 @@ __global__ void __launch_bounds__(kMergeThreads) vos_merge_writeback(const Merge
         float best_v = -INFINITY;
         float* mrec = prm.meta + (static_cast<size_t>(prm.q_slot) * prm.p_pad + pix) * kMetaFloats + 2;
 #pragma unroll
-        for (int k = 0; k < kMaxClasses; ++k) {
+        for (int k = 0; k < kCap; ++k) {
             if (k < prm.d) {
                 const float pk = acc[k] * inv;
                 acc[k] = pk;
@@ -567,9 +569,11 @@ __global__ void __launch_bounds__(kMergeThreads) vos_merge_writeback(const Merge
             }
         }
         if (prm.write_labels) {
+            if constexpr (kCap <= kMetaClasses) {   // wider class sets live in the class bytes only
 #pragma unroll
-            for (int k = 0; k < kMaxClasses; ++k)
-                mrec[k] = (k < prm.d) ? (prm.probability ? acc[k] : (k == best ? 1.f : 0.f)) : 0.f;
+                for (int k = 0; k < kCap; ++k)
+                    mrec[k] = (k < prm.d) ? (prm.probability ? acc[k] : (k == best ? 1.f : 0.f)) : 0.f;
+            }
             prm.cls[static_cast<size_t>(prm.q_slot) * prm.p_pad + pix] = static_cast<uint8_t>(best);
         }
         if (prm.out_mask_lowres) prm.out_mask_lowres[pix] = static_cast<uint8_t>(best);
@@ -704,14 +708,15 @@ __global__ void vos_init_meta(float* __restrict__ meta, int slots, int p_pad, in
 }
 
 __global__ void vos_set_labels_index(float* __restrict__ meta_slot, uint8_t* __restrict__ cls_slot,
-                                     const uint8_t* __restrict__ cls, int n_pixels) {
+                                     const uint8_t* __restrict__ cls, int n_pixels, int d) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pixels) return;
     const int c = cls[p];
     cls_slot[p] = static_cast<uint8_t>(c);
+    if (d > kMetaClasses) return;   // more classes than a meta record holds: class bytes only
     float* rec = meta_slot + static_cast<size_t>(p) * kMetaFloats + 2;
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) rec[k] = (k == c) ? 1.f : 0.f;
+    for (int k = 0; k < kMetaClasses; ++k) rec[k] = (k == c) ? 1.f : 0.f;
 }
 
 __global__ void vos_set_labels_dense(float* __restrict__ meta_slot, const float* __restrict__ labels, int n_pixels, int d) {
@@ -719,7 +724,7 @@ __global__ void vos_set_labels_dense(float* __restrict__ meta_slot, const float*
     if (p >= n_pixels) return;
     float* rec = meta_slot + static_cast<size_t>(p) * kMetaFloats + 2;
 #pragma unroll
-    for (int k = 0; k < kMaxClasses; ++k) rec[k] = (k < d) ? labels[static_cast<size_t>(k) * n_pixels + p] : 0.f;
+    for (int k = 0; k < kMetaClasses; ++k) rec[k] = (k < d) ? labels[static_cast<size_t>(k) * n_pixels + p] : 0.f;
 }
 
 }  // namespace vosk

@@ -170,7 +170,15 @@ int dispatch_affinity(vosprop_engine* e, const vosk::AffinityParams& prm, int gr
     if (d <= 6) return launch_affinity<6>(e, prm, grid, kernel, st);
     if (d <= 8) return launch_affinity<8>(e, prm, grid, kernel, st);
     if (d <= 11) return launch_affinity<11>(e, prm, grid, kernel, st);
-    return launch_affinity<14>(e, prm, grid, kernel, st);
+    if (d <= vosk::kMetaClasses) return launch_affinity<14>(e, prm, grid, kernel, st);
+    // 15..24 classes: index-label kernel only (vosprop_propagate has checked that)
+    const bool split = prm.feat_fmt == vosk::kFmtSplit;
+    void (*kern)(CUtensorMap, CUtensorMap, vosk::AffinityParams) =
+        split ? vosk::vos_affinity_idx<vosk::kMaxClasses, true, true> : vosk::vos_affinity_idx<vosk::kMaxClasses, false, true>;
+    VOS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kIdxSmem));
+    VOS_CUDA(launch_pdl(kern, grid, vosk::kIdxThreads, vosk::kIdxSmem, st, e->tmap_hi, e->tmap_lo, prm));
+    VOS_CUDA(cudaGetLastError());
+    return VOSPROP_OK;
 }
 
 int check_frame(const vosprop_engine* e, int frame_idx) {
@@ -428,7 +436,7 @@ int vosprop_set_labels_index(vosprop_engine* e, int32_t frame_idx, const uint8_t
     if (rc) return rc;
     if (!class_idx) return fail(VOSPROP_ERR_INVALID, "null class_idx");
     uint8_t* cls_slot = e->cls + static_cast<size_t>(frame_idx % e->cfg.ring_slots) * e->p_pad;
-    vosk::vos_set_labels_index<<<(e->P + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(ms, cls_slot, class_idx, e->P);
+    vosk::vos_set_labels_index<<<(e->P + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(ms, cls_slot, class_idx, e->P, e->d);
     VOS_CUDA(cudaGetLastError());
     e->launches++;
     return VOSPROP_OK;
@@ -436,6 +444,8 @@ int vosprop_set_labels_index(vosprop_engine* e, int32_t frame_idx, const uint8_t
 
 int vosprop_set_labels_dense(vosprop_engine* e, int32_t frame_idx, const float* labels, void* stream) {
     float* ms = nullptr;
+    if (e && e->d > VOSPROP_MAX_DENSE_CLASSES)
+        return fail(VOSPROP_ERR_UNSUPPORTED, "dense labels hold at most %d classes (d=%d): use index labels", VOSPROP_MAX_DENSE_CLASSES, e->d);
     int rc = labels_target(e, frame_idx, &ms, 2);
     if (rc) return rc;
     if (!labels) return fail(VOSPROP_ERR_INVALID, "null labels");
@@ -492,6 +502,9 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     // (dense / probability labels, tiny maps) runs on the general tensor-core kernel
     int kernel = s->kernel;
     if (kernel == VOSPROP_KERNEL_TC && (!all_index || e->W_d < 32)) kernel = VOSPROP_KERNEL_TC_DENSE;
+    if (e->d > VOSPROP_MAX_DENSE_CLASSES && (kernel != VOSPROP_KERNEL_TC || s->topk > 0 || s->probability_propagation))
+        return fail(VOSPROP_ERR_UNSUPPORTED, "d=%d > %d classes runs only on the index-label kernel: index labels, W_d >= 32 (got %d), "
+                    "topk = 0, no probability propagation", e->d, VOSPROP_MAX_DENSE_CLASSES, e->W_d);
     const vosd::Decomp dec = vosd::make_decomp(e->P, s->n_refs, e->num_sms);
     if (static_cast<size_t>(dec.grid) * dec.max_segs * vosk::kIdxSub > e->partial_records)
         return fail(VOSPROP_ERR_UNSUPPORTED, "partial buffer too small (grid %d x segs %d)", dec.grid, dec.max_segs);
@@ -525,7 +538,8 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     mp.out_prediction = s->out_prediction; mp.out_mask_lowres = s->out_mask_lowres; mp.out_mask_fullres = s->out_mask_fullres;
     {
         TimedLaunch timed(e, VOSPROP_T_MERGE, st);
-        VOS_CUDA(launch_pdl(vosk::vos_merge_writeback, e->H_d, vosk::kMergeThreads, e->W_d, st, mp));
+        VOS_CUDA(launch_pdl(e->d > vosk::kMetaClasses ? vosk::vos_merge_writeback<vosk::kMaxClasses> : vosk::vos_merge_writeback<vosk::kMetaClasses>,
+                            e->H_d, vosk::kMergeThreads, e->W_d, st, mp));
     }
     VOS_CUDA(cudaGetLastError());
     if (s->write_labels) e->slot_labels[q_slot] = s->probability_propagation ? 2 : 1;

@@ -1,5 +1,5 @@
 """CLI entry point with the reference's command names (main.py:12-23).  Only the commands on or
-next to the propagation hot path are registered: `inference` (built) and `validation` (next)."""
+next to the propagation hot path are registered: `inference` and `validation`."""
 import click
 
 from src.inference import inference_command

@@ -1,13 +1,63 @@
-"""InferenceDataset: the caller side of the hot path (reference src/utils/datasets.py:111-167).
-One frame per item, `(normalised CHW tensor, video_name)`; frames are grouped by sub-directory."""
+"""The datasets either side of the propagation path (reference src/utils/datasets.py).
+InferenceDataset (datasets.py:111-167): one frame per item, `(normalised CHW tensor, video_name)`; frames are grouped
+by sub-directory.  TrainDataset (datasets.py:19-109): clips of `frame_num` consecutive frames of one video, all cropped
+and flipped the same way, with their RGB annotations -- what `validation` feeds to the loss."""
 from io import BytesIO
 from pathlib import Path
 
 import numpy as np
+import torch
 from loguru import logger
 from PIL import Image, ImageOps
 from torchvision import datasets, transforms
+from torchvision.datasets.folder import make_dataset
 from tqdm import tqdm
+
+from src.utils.transforms import crop, get_crop_params
+
+_NORMALIZE = dict(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])
+
+
+class TrainDataset(datasets.ImageFolder):
+    """Item = (frames (T,3,c,c) fp32 normalised, annotations (T,3,c,c) fp32 RGB 0..255, video index).  RNG draws per
+    item, in the reference's order (datasets.py:72-86): horizontal flip, vertical flip, then the crop origin."""
+
+    def __init__(self, img_root, annotation_root, cropping=256, frame_num=10, transform=None, target_transform=None,
+                 color_jitter=False):
+        super().__init__(img_root, transform=transform, target_transform=target_transform)
+        if color_jitter:
+            raise NotImplementedError('colour jitter is a training-time augmentation; validation runs without it')
+        self.annotations = make_dataset(annotation_root, self.class_to_idx, extensions=('png', 'jpg', 'jpeg'))
+        self.cropping, self.frame_num, self.color_jitter = cropping, frame_num, color_jitter
+        self.rgb_normalize = transforms.Compose([transforms.ToTensor(), transforms.Normalize(**_NORMALIZE)])
+        logger.info(f'Loading {len(self.imgs)} train images and annotations.')
+        self.img_bytes = [Path(p).read_bytes() for p, _ in tqdm(self.imgs)]
+        self.annotation_bytes = [Path(p).read_bytes() for p, _ in tqdm(self.annotations)]
+
+    def _one_video(self, index):
+        return self.imgs[index][1] == self.imgs[index + self.frame_num - 1][1]
+
+    def __getitem__(self, index):
+        T = self.frame_num
+        index = min(index, len(self.imgs) - T)      # clips never run past the end of the dataset ...
+        while not self._one_video(index):           # ... nor across a video boundary
+            index -= 1
+        h_flip = torch.rand(size=(1,)).item() < 0.5
+        v_flip = torch.rand(size=(1,)).item() < 0.5
+        frames, annotations, window = [], [], None
+        for i in range(T):
+            img = Image.open(BytesIO(self.img_bytes[index + i])).convert('RGB')
+            ann = Image.open(BytesIO(self.annotation_bytes[index + i])).convert('RGB')
+            if h_flip:
+                img, ann = img.transpose(Image.FLIP_LEFT_RIGHT), ann.transpose(Image.FLIP_LEFT_RIGHT)
+            if v_flip:
+                img, ann = img.transpose(Image.FLIP_TOP_BOTTOM), ann.transpose(Image.FLIP_TOP_BOTTOM)
+            if window is None:
+                window = get_crop_params(img.size, self.cropping)
+            frames.append(self.rgb_normalize(crop(img, *window)).numpy())
+            annotations.append(np.asarray(crop(ann, *window)).transpose(2, 0, 1))
+        return (torch.from_numpy(np.asarray(frames)).float(), torch.from_numpy(np.asarray(annotations)).float(),
+                self.imgs[index + T - 1][1])
 
 
 class InferenceDataset(datasets.ImageFolder):

@@ -17,6 +17,29 @@ def index_to_onehot(idx, d):
     return torch.zeros(d, idx.shape[1], device=Config.DEVICE).scatter_(0, idx.to(Config.DEVICE), 1)
 
 
+def color_to_class(img, centroids):
+    """RGB annotation (B,3,H,W) float -> (B,H,W) long index of the nearest centroid (utils.py:45-56; Euclidean, the
+    first minimum wins).  The squared distances are small integers, exact in fp32, so skipping the reference's sqrt
+    cannot change an arg-min."""
+    B, C, H, W = img.shape
+    px = img.permute(0, 2, 3, 1).reshape(-1, 1, C)
+    d2 = ((px - centroids.to(px.device).reshape(1, -1, C)) ** 2).sum(2)
+    return d2.argmin(1).reshape(B, H, W)
+
+
+def annotation_centroids():
+    """The 22 annotation colours the reference ships as ./annotation_centroids.npy (loaded from the working directory,
+    validation.py:75): the first 22 DAVIS palette entries with 192 at 191 (k-means output).  Used when that file is not
+    in the working directory."""
+    table = np.zeros((22, 3), dtype=np.int32)
+    for k in range(22):
+        for bit in range(8):
+            for ch in range(3):
+                table[k, ch] |= ((k >> (3 * bit + ch)) & 1) << (7 - bit)
+    table[table == 192] = 191
+    return table
+
+
 def _read_checkpoint(model, checkpoint):
     if checkpoint is None:
         return model

@@ -5,7 +5,8 @@ import ctypes as C
 from pathlib import Path
 
 MAX_REFS = 32
-MAX_CLASSES = 14
+MAX_CLASSES = 24
+MAX_DENSE_CLASSES = 14
 MAX_TOPK = 64
 FEAT_DIM = 256
 F32, F16, BF16 = 0, 1, 2

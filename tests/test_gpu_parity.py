@@ -181,7 +181,7 @@ def test_error_paths():
         eng.append(0, torch.zeros(256, 12, 20, device='cuda'))
     eng.append(0, torch.zeros(256, 12, 20, device='cuda', dtype=torch.float16))
     with pytest.raises(VosPropError):
-        eng.reset(12, 20, 96, 160, 15)  # too many classes
+        eng.reset(12, 20, 96, 160, 25)  # too many classes (15..24 run on the index-label kernel only)
     with pytest.raises(VosPropError):
         eng.reset(120, 200, 960, 1600, 3)  # beyond capacity
     torch.cuda.synchronize()

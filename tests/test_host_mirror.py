@@ -95,8 +95,11 @@ def test_cli_surface():
     import main
     r = CliRunner().invoke(main.cli, ['--help'])
     assert 'inference' in r.output and 'validation' in r.output
-    r = CliRunner().invoke(main.cli, ['validation'])
-    assert r.exit_code != 0 and 'N1' in r.output
+    r = CliRunner().invoke(main.cli, ['validation', '--help'])
+    for opt in ('--data', '--checkpoints', '--bs', '--loss', '--miner', '--margin', '--loss_weight', '--output'):
+        assert opt in r.output                       # the reference's options (src/validation.py:30-42)
+    r = CliRunner().invoke(main.cli, ['validation', '-d', '.', '-c', '.', '-o', 'x.json', '--loss', 'triplet'])
+    assert r.exit_code != 0 and 'not built' in r.output
 
 
 def test_lpt_assignment_is_balanced_and_deterministic():
