@@ -114,6 +114,14 @@ int vosprop_reset(vosprop_engine* e, int32_t H_d, int32_t W_d, int32_t H, int32_
 int vosprop_append_features(vosprop_engine* e, int32_t frame_idx, const void* features,
                             int32_t dtype, int32_t layout, void* stream);
 
+/* Append `n_frames` consecutive frames first_frame_idx .. +n_frames-1 in one call: `features` holds n_frames maps
+ * back to back (each K x P or P x K elements of `dtype`); when `class_idx` is not NULL it holds n_frames x P class
+ * bytes and every appended frame also gets its index labels.  Same effect as n_frames x (vosprop_append_features
+ * [+ vosprop_set_labels_index]); it exists for callers that install a whole labelled clip at once -- the reference
+ * frames of a validation clip (src/train.py:181-207: ref = features[:, 0:num_frames-1] with their annotations). */
+int vosprop_append_frames(vosprop_engine* e, int32_t first_frame_idx, int32_t n_frames, const void* features,
+                          int32_t dtype, int32_t layout, const uint8_t* class_idx, void* stream);
+
 /* Set frame `frame_idx`'s labels from a class-index map (device, P x uint8): the one-hot first
  * frame of get_labels (predict.py:92-96).  */
 int vosprop_set_labels_index(vosprop_engine* e, int32_t frame_idx, const uint8_t* class_idx, void* stream);

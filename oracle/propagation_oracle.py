@@ -321,6 +321,29 @@ def propagate_two_streams(strategy: str, feats_a: torch.Tensor, feats_b: torch.T
     return torch.stack(out).to(torch.uint8)
 
 
+THREE_SCALE_OUT = (480, 910)     # inference_utils.py:574 -- hard-coded, whatever the input size
+
+
+def propagate_three_scales(feats_by_scale: Sequence[torch.Tensor], first_label_full: np.ndarray, scale: float = 1.15,
+                           sigma_1: float = 8.0, sigma_2: float = 21.0, frame_range: int = 40, ref_num: int = 9,
+                           temperature: float = 1.0, probability_propagation: bool = False) -> torch.Tensor:
+    """inference_3_scale (src/utils/inference_utils.py:514-595) with the feature extractor factored out: three
+    independent single-stream propagations on inputs nearest-resized by 0.9 / 1.0 / `scale` (first-frame labels sampled
+    at ceil(H * 0.125 * s), predict.py:146-153), every prediction nearest-up-sampled to 480 x 910 and arg-maxed, the three
+    label maps fused by an element-wise maximum of the class indices (:594).  -> (T-1, 480, 910) uint8."""
+    H, W = first_label_full.shape
+    lab = np.asarray(first_label_full)
+    _, d = first_frame_labels(lab)
+    fused = None
+    for feats, s in zip(feats_by_scale, (0.9, 1.0, scale)):
+        low, _ = first_frame_labels(lab, d, dims=(int(np.ceil(H * SCALE * s)), int(np.ceil(W * SCALE * s))))
+        ups = _propagate_stream(feats, low, d, THREE_SCALE_OUT, sigma_1, sigma_2, frame_range, ref_num, temperature,
+                                probability_propagation)
+        masks = torch.stack([torch.argmax(u, 1)[0] for u in ups])
+        fused = masks if fused is None else torch.maximum(fused, masks)
+    return fused.to(torch.uint8)
+
+
 # --------------------------------------------------------------------------------------
 # bf16 hi/lo split emulation (what the tcgen05 kernel feeds the tensor cores) -- used by tests
 # to bound the error budget, not a reference behaviour.

@@ -191,6 +191,50 @@ def run_inference_two_streams(ref, strategy, feats_a, feats_b, first_label_full,
     return masks.astype(np.uint8)
 
 
+def run_inference_3_scale(ref, feats_by_video, firsts, palette, workdir, size, scale=1.15, sigma_1=8.0, sigma_2=21.0,
+                          frame_range=40, ref_num=9, temperature=1.0, probability_propagation=False):
+    """Drive the reference's REAL ``inference_3_scale`` (src/utils/inference_utils.py:514-595) with a table-lookup
+    model.  feats_by_video: {video: [feats at 0.9, feats at 1.0, feats at `scale`]}, each (T,K,h,w); firsts: {video:
+    first annotation (H,W)}; size = (H,W) of the loader's frames.  The model is keyed by the (nearest-resized) input's
+    shape and by the frame / video number encoded in the input.  Returns {video: (T-1, 480, 910) uint8 masks read back
+    from the PNGs} -- the output size is hard-coded in the reference (:574)."""
+    import numpy as np
+    import torch
+    from PIL import Image
+
+    H, W = size
+    workdir = Path(workdir)
+    ann_dir = workdir / 'Annotations' / '480p'
+    videos = sorted(feats_by_video)
+    for v in videos:
+        (ann_dir / v).mkdir(parents=True, exist_ok=True)
+        img = Image.fromarray(firsts[v].astype(np.uint8), mode='P')
+        img.putpalette(palette)
+        img.save(ann_dir / v / '00000.png')
+    save = workdir / 'out'
+    by_shape = {}
+    for k, s in enumerate((0.9, 1.0, scale)):
+        by_shape[(int(np.ceil(H * s)), int(np.ceil(W * s)))] = k
+    assert len(by_shape) == 3
+
+    def model(inp):
+        k = by_shape[tuple(inp.shape[2:])]
+        v, t = int(inp[0, 0, 0, 0].item()) // 1000, int(inp[0, 0, 0, 0].item()) % 1000
+        return feats_by_video[videos[v]][k][t][None]
+
+    loader = [(torch.full((1, 1, H, W), float(1000 * vi + t)), (v,)) for vi, v in enumerate(videos)
+              for t in range(feats_by_video[v][0].shape[0])]
+    iu = ref.inference_utils
+    with torch.no_grad():
+        iu.inference_3_scale(model, loader, len(loader), ann_dir, videos[0], str(save), sigma_1, sigma_2, frame_range,
+                             ref_num, temperature, probability_propagation, scale, True)
+    out = {}
+    for v in videos:
+        T = feats_by_video[v][0].shape[0]
+        out[v] = np.stack([np.asarray(Image.open(save / v / f'{t:05d}.png')) for t in range(1, T)]).astype(np.uint8)
+    return out
+
+
 def default_palette():
     pal = [0, 0, 0, 128, 0, 0, 0, 128, 0, 128, 128, 0, 0, 0, 128, 128, 0, 128, 0, 128, 128,
            128, 128, 128, 64, 0, 0, 192, 0, 0, 64, 128, 0, 192, 128, 0]

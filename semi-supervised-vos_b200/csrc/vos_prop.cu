@@ -442,6 +442,24 @@ int vosprop_set_labels_index(vosprop_engine* e, int32_t frame_idx, const uint8_t
     return VOSPROP_OK;
 }
 
+int vosprop_append_frames(vosprop_engine* e, int32_t first_frame_idx, int32_t n_frames, const void* features, int32_t dtype,
+                          int32_t layout, const uint8_t* class_idx, void* stream) {
+    if (!e) return fail(VOSPROP_ERR_INVALID, "null engine");
+    if (n_frames < 0 || n_frames > e->cfg.ring_slots)
+        return fail(VOSPROP_ERR_INVALID, "n_frames=%d outside 0..ring_slots=%d", n_frames, e->cfg.ring_slots);
+    if (dtype != VOSPROP_F32 && dtype != VOSPROP_F16 && dtype != VOSPROP_BF16) return fail(VOSPROP_ERR_INVALID, "unknown dtype %d", dtype);
+    const size_t frame_bytes = static_cast<size_t>(VOSPROP_FEAT_DIM) * e->P * (dtype == VOSPROP_F32 ? 4 : 2);
+    for (int i = 0; i < n_frames; ++i) {
+        int rc = vosprop_append_features(e, first_frame_idx + i, static_cast<const char*>(features) + i * frame_bytes, dtype, layout, stream);
+        if (rc) return rc;
+        if (class_idx) {
+            rc = vosprop_set_labels_index(e, first_frame_idx + i, class_idx + static_cast<size_t>(i) * e->P, stream);
+            if (rc) return rc;
+        }
+    }
+    return VOSPROP_OK;
+}
+
 int vosprop_set_labels_dense(vosprop_engine* e, int32_t frame_idx, const float* labels, void* stream) {
     float* ms = nullptr;
     if (e && e->d > VOSPROP_MAX_DENSE_CLASSES)

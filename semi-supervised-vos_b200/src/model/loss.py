@@ -35,14 +35,12 @@ def propagate_clips(ref, target, ref_cls, d, temperature=1.0):
     eng.reset(H, W, H * 8, W * 8, d, precision_for(ref.dtype))
     out = torch.empty((B, d, H * W), dtype=torch.float32, device=ref.device)
     cls8 = ref_cls.to(device=ref.device, dtype=torch.uint8)
-    refs, zeros = list(range(R)), [0.0] * R
+    zeros = [0.0] * R
     for b in range(B):
         base = (b % 2) * (R + 1)                 # alternate between two slot groups of the ring
-        for r in range(R):
-            eng.append(base + r, ref[b, r])
-            eng.set_labels_index(base + r, cls8[b, r])
+        eng.append_frames(base, ref[b], cls8[b])     # the clip's labelled reference frames, one call
         eng.append(base + R, target[b])
-        eng.propagate(base + R, [base + r for r in refs], zeros, temperature, False, write_labels=False,
+        eng.propagate(base + R, list(range(base, base + R)), zeros, temperature, False, write_labels=False,
                       want_prediction=False, want_lowres=False, want_fullres=False, out_prediction=out[b])
     return out
 

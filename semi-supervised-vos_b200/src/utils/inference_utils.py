@@ -56,13 +56,17 @@ class _VideoSink:
         self.fill += 1
         return self.chunks[-1][self.fill - 1]
 
-    def flush(self):
+    def stacked(self) -> torch.Tensor:
+        """(frames, H, W) uint8 on the device."""
+        return torch.cat([c for c in self.chunks[:-1]] + [self.chunks[-1][:self.fill]], 0)
+
+    def flush(self, dev_masks=None):
         """One D2H copy into pinned memory, then PNG encoding on a writer thread: the next video's propagation does
         not wait for the files of this one (reference: save_predictions on the critical path, inference_utils.py:30)."""
         if not self.chunks:
             return
-        parts = [c for c in self.chunks[:-1]] + [self.chunks[-1][:self.fill]]
-        dev_masks = torch.cat(parts, 0)
+        if dev_masks is None:
+            dev_masks = self.stacked()
         host = torch.empty(dev_masks.shape, dtype=torch.uint8, pin_memory=True)
         host.copy_(dev_masks, non_blocking=True)
         done = torch.cuda.Event()
@@ -285,7 +289,60 @@ def inference_multimodel(model, additional_model, inference_loader, total_len, a
                            disable, 'multimodel')
 
 
-def inference_3_scale(*args, **kwargs):
-    raise NotImplementedError(
-        "inference strategy '3-scale' (reference src/utils/inference_utils.py:514-595) re-runs the whole loader at "
-        "scales 0.9 / 1.0 / s with a hard-coded (480, 910) output size; it is not built (SURVEY.md section 8f, row N2)")
+THREE_SCALE_OUT = (480, 910)     # the reference up-samples every scale's prediction to this size, whatever the input
+
+
+def inference_3_scale(model, inference_loader, total_len, annotation_dir, last_video, save, sigma_1, sigma_2,
+                      frame_range, ref_num, temperature, probability_propagation, scale, disable):
+    """Reference: src/utils/inference_utils.py:514-595.  Three passes over the loader with the frames nearest-resized
+    by 0.9 / 1.0 / `scale`; each pass is a plain single-memory propagation whose label maps are written at 480 x 910
+    (hard-coded there, :574; kept, because the drop-in must write the files the reference writes); the three label maps
+    of a frame are fused by an element-wise maximum of the class indices (:594).  The running maximum stays on the
+    device; a video's PNGs are queued as soon as its third pass ends."""
+    H_out, W_out = THREE_SCALE_OUT
+    slots = required_ring_slots(frame_range, ref_num)
+    fused, palettes = {}, {}
+    scales = (0.9, 1.0, scale)
+    for k, s in enumerate(scales):
+        frame_idx, sink, engine, current = 0, None, None, None
+
+        def finish(sink):
+            masks = sink.stacked()
+            fused[sink.video] = masks if k == 0 else torch.maximum(fused[sink.video], masks)
+            if k == len(scales) - 1:
+                sink.flush(fused.pop(sink.video))
+
+        for input, (current_video,) in tqdm(inference_loader, total=total_len, disable=disable):
+            (_, _, H, W) = input.shape
+            size = (int(np.ceil(H * s)), int(np.ceil(W * s)))
+            input = torch.nn.functional.interpolate(input.to(Config.DEVICE, non_blocking=True), size=size, mode='nearest')
+            if current is not None and current_video != current:
+                finish(sink)
+                frame_idx = 0
+            current = current_video
+            with torch.autocast('cuda', dtype=torch.float16):
+                features = model(input)
+            if frame_idx == 0:
+                first_annotation = annotation_dir / current_video / '00000.png'
+                label_1hot, d, palette, _, _ = prepare_first_frame(
+                    current_video, save, first_annotation, sigma_1, sigma_2, inference_strategy='3-scale',
+                    probability_propagation=probability_propagation, scale=s)
+                (_, _, H_d, W_d) = features.shape
+                if label_1hot.shape[-1] != H_d * W_d:
+                    raise ValueError(f'scale {s}: the network maps {size} to {(H_d, W_d)} but the annotation is sampled '
+                                     f'at {label_1hot.shape[-1]} pixels (the reference fails on such sizes too)')
+                engine = _engine_for(H_d * W_d, slots)
+                engine.reset(H_d, W_d, H_out, W_out, int(d), precision_for(features.dtype))
+                engine.append(0, features)
+                engine.set_labels_index(0, label_1hot[:, 0].argmax(0))
+                palettes.setdefault(current_video, palette)
+                sink = _VideoSink(current_video, palettes[current_video], save, H_out, W_out, features.device)
+                frame_idx += 1
+                continue
+            engine.append(frame_idx, features)
+            engine.step(frame_idx, frame_range, ref_num, sigma_1, sigma_2, temperature, probability_propagation,
+                        want_prediction=False, want_lowres=False, want_fullres=False, out_fullres=sink.next_slot())
+            frame_idx += 1
+        if sink is not None:
+            finish(sink)
+    _WRITER.drain()

@@ -132,6 +132,28 @@ class PropagationEngine:
                                                      _DTYPES[features.dtype], layout, self._stream()))
         features.record_stream(torch.cuda.current_stream(self.device))
 
+    def append_frames(self, first_frame_idx: int, features: torch.Tensor, class_idx: Optional[torch.Tensor] = None):
+        """features: (n,K,H_d,W_d) contiguous fp32/fp16/bf16 -> frames first_frame_idx .. +n-1; class_idx: optional
+        (n,H_d,W_d) / (n,P) uint8 index labels for all of them (one call installs a labelled clip)."""
+        H_d, W_d = self.geom[0], self.geom[1]
+        n = features.shape[0]
+        if tuple(features.shape[1:]) != (capi.FEAT_DIM, H_d, W_d):
+            raise ValueError(f'expected (n,{capi.FEAT_DIM},{H_d},{W_d}) features, got {tuple(features.shape)}')
+        if features.dtype not in _DTYPES or not features.is_cuda:
+            raise TypeError(f'features must be a CUDA fp32/fp16/bf16 tensor, got {features.dtype} on {features.device}')
+        features = features.contiguous()
+        cls_ptr = None
+        if class_idx is not None:
+            class_idx = class_idx.reshape(n, -1).to(device=self.device, dtype=torch.uint8).contiguous()
+            if class_idx.shape[1] != H_d * W_d:
+                raise ValueError(f'expected {H_d * W_d} labels per frame, got {class_idx.shape[1]}')
+            cls_ptr = C.c_void_p(class_idx.data_ptr())
+        capi.check(self._lib.vosprop_append_frames(self._h, first_frame_idx, n, C.c_void_p(features.data_ptr()),
+                                                   _DTYPES[features.dtype], capi.NCHW, cls_ptr, self._stream()))
+        features.record_stream(torch.cuda.current_stream(self.device))
+        if class_idx is not None:
+            class_idx.record_stream(torch.cuda.current_stream(self.device))
+
     def set_labels_index(self, frame_idx: int, class_idx: torch.Tensor):
         P = self.geom[0] * self.geom[1]
         class_idx = class_idx.reshape(-1).to(device=self.device, dtype=torch.uint8).contiguous()

@@ -87,6 +87,45 @@ def test_two_stream_strategies_write_the_reference_pngs(name, tmp_path, mirror):
     assert agree >= 0.999
 
 
-def test_three_scale_names_the_missing_row(mirror):
-    with pytest.raises(NotImplementedError, match='3-scale'):
-        mirror.inference_3_scale()
+@pytest.mark.parametrize('name', ['three_scale', 'three_scale_prob'])
+def test_three_scale_writes_the_reference_pngs(name, tmp_path, mirror):
+    """inference_3_scale against the PNGs the reference's own inference_3_scale wrote (oracle/make_golden_3scale.py):
+    two videos, three passes over the loader, 480 x 910 outputs, element-wise maximum of the class indices."""
+    import json
+    from oracle import propagation_oracle as O
+    cfg = json.loads((G.GOLDEN / 'meta_3scale.json').read_text())[name]
+    want = np.load(G.GOLDEN / f'tta_{name}.npz')
+    H, W, scale = cfg['H'], cfg['W'], cfg['scale']
+    feats, by_shape, videos = {}, {}, [v['name'] for v in cfg['videos']]
+    ann_dir = None
+    for v in cfg['videos']:
+        per_scale = []
+        for k, s in enumerate((0.9, 1.0, scale)):
+            Hs, Ws = int(np.ceil(H * s)), int(np.ceil(W * s))
+            f, lab = O.synthetic_sequence(v['T'], Hs, Ws, v['objects'], seed=v['seed'], feat_scale=0.30)
+            per_scale.append(f.cuda())
+            by_shape[(Hs, Ws)] = k
+            if s == 1.0:
+                first = lab
+        feats[v['name']] = per_scale
+        (tmp_path / 'Annotations' / '480p' / v['name']).mkdir(parents=True)
+        img = Image.fromarray(first.astype(np.uint8), mode='P')
+        img.putpalette(RH.default_palette())
+        img.save(tmp_path / 'Annotations' / '480p' / v['name'] / '00000.png')
+    ann_dir, save = tmp_path / 'Annotations' / '480p', tmp_path / 'out'
+
+    def model(inp):
+        code = int(inp[0, 0, 0, 0].item())
+        return feats[videos[code // 1000]][by_shape[tuple(inp.shape[2:])]][code % 1000][None]
+
+    loader = [(torch.full((1, 1, H, W), float(1000 * vi + t)), (v['name'],)) for vi, v in enumerate(cfg['videos'])
+              for t in range(v['T'])]
+    with torch.no_grad():
+        mirror.inference_3_scale(model, loader, len(loader), ann_dir, videos[0], str(save), 8.0, 21.0, 40, 9, 1.0,
+                                 cfg['probability_propagation'], scale, True)
+    for v in cfg['videos']:
+        masks = _read_masks(save, v['name'], v['T'])
+        assert masks.shape == want[v['name']].shape == (v['T'] - 1, 480, 910)
+        agree = float((masks == want[v['name']]).mean())
+        print(f"3-scale/{name}/{v['name']}: mask agreement {agree:.6f}")
+        assert agree >= 0.999

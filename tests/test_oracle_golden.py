@@ -125,3 +125,22 @@ def test_ref_sigmas_matches_slice_semantics():
     assert O.ref_sigmas(16, 9, 8.0, 21.0) == [21.0] * 5 + [8.0] * 4
     assert O.ref_sigmas(20, 3, 8.0, 21.0) == [8.0] * 3
     assert O.ref_sigmas(20, 4, 8.0, 21.0) == [8.0] * 4
+
+
+@pytest.mark.parametrize('name', ['three_scale', 'three_scale_prob'])
+def test_three_scale_oracle_matches_reference_pngs(name):
+    """oracle.propagate_three_scales against the PNGs the reference's inference_3_scale wrote
+    (src/utils/inference_utils.py:514-595; oracle/make_golden_3scale.py)."""
+    import json
+    cfg = json.loads((G.GOLDEN / 'meta_3scale.json').read_text())[name]
+    want = np.load(G.GOLDEN / f'tta_{name}.npz')
+    v = cfg['videos'][-1]                       # one video keeps the CPU suite short
+    feats = []
+    for s in (0.9, 1.0, cfg['scale']):
+        f, lab = O.synthetic_sequence(v['T'], int(np.ceil(cfg['H'] * s)), int(np.ceil(cfg['W'] * s)), v['objects'],
+                                      seed=v['seed'], feat_scale=0.30)
+        feats.append(f)
+        if s == 1.0:
+            first = lab
+    got = O.propagate_three_scales(feats, first, cfg['scale'], probability_propagation=cfg['probability_propagation'])
+    assert np.array_equal(got.numpy(), want[v['name']])
