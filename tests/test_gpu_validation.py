@@ -130,6 +130,32 @@ class _Float64(torch.nn.Module):
         return self.inner(x.double()).float()
 
 
+def test_append_frames_equals_per_frame_appends():
+    """vosprop_append_frames (a labelled clip in one call) leaves the engine in the state n x (append + set_labels_index)
+    leaves it in: the propagated distribution is bit-identical."""
+    from vosb200 import PropagationEngine, VosPropError
+    feats, cls = V.synthetic_batch(1, T=6, seed=9, half=True)
+    f, c = feats[0].cuda().half(), cls[0].cuda().to(torch.uint8)
+    outs = []
+    for batched in (False, True):
+        eng = PropagationEngine(max_pixels=1024, ring_slots=12)
+        eng.reset(32, 32, 256, 256, 22, 1)
+        if batched:
+            eng.append_frames(0, f[:5], c[:5])
+        else:
+            for t in range(5):
+                eng.append(t, f[t])
+                eng.set_labels_index(t, c[t])
+        eng.append(5, f[5])
+        outs.append(eng.propagate(5, list(range(5)), [0.0] * 5, write_labels=False)['prediction'].clone())
+    assert torch.equal(outs[0], outs[1])
+    with pytest.raises(VosPropError):
+        eng.append_frames(0, torch.zeros(13, 256, 32, 32, device='cuda', dtype=torch.float16))     # more frames than ring slots
+    with pytest.raises(ValueError):
+        eng.append_frames(0, f[:2], c[:3].reshape(3, -1)[:, :100])
+    torch.cuda.synchronize()
+
+
 def _loader(root, bs):
     from src.utils.datasets import TrainDataset
     ds = TrainDataset(root / 'JPEGImages/480p', root / 'Annotations/480p', frame_num=10, color_jitter=False)
