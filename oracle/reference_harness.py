@@ -10,8 +10,8 @@ are applied to the *environment*, never to the reference's sources:
   1. ``numpy.int``            (src/model/predict.py:85, src/utils/datasets.py:145)
   2. ``PIL.Image.ANTIALIAS``  (src/utils/datasets.py:146)
   3. ``model_zoo.load_url``   (src/model/backbone/resnet.py:194 -- pretrained download, no network)
-  4. ``skimage.morphology``   (src/model/triplet_miners.py:15 -- not installed here; only the skeleton miners call it,
-                               the validation golden uses CrossEntropy) -- see import_validation()
+  4. ``skimage.morphology``   (src/model/triplet_miners.py:15, src/utils/metrics.py:6-7 -- not installed here) -- see
+                               _skimage_shim()
 """
 from __future__ import annotations
 
@@ -66,25 +66,60 @@ def import_reference(device: str = 'cpu'):
     return ns
 
 
+def _skimage_shim():
+    """Shim 4: scikit-image is not installed here.  The reference imports it for (a) `skeletonize` (skeleton triplet miners
+    only -- never called by the goldens) and (b) one grey dilation with a disk footprint in the F-measure
+    (src/utils/metrics.py:92-94).  (b) is restated with scipy: `disk(r)` = {x^2 + y^2 <= r^2} on -r..r and
+    `dilation(img, fp)` = maximum over the footprint with the image border padded by the minimum (scikit-image's documented
+    behaviour); goldens that depend on it say so."""
+    import types
+    if 'skimage' in sys.modules:
+        return
+    try:
+        importlib.import_module('skimage.morphology')
+        return
+    except ImportError:
+        pass
+    import numpy as np
+    from scipy import ndimage
+    sk, mo = types.ModuleType('skimage'), types.ModuleType('skimage.morphology')
+
+    def skeletonize(*a, **k):
+        raise RuntimeError('skimage is not installed: the skeleton miners cannot run in this container')
+
+    def disk(radius, dtype=np.uint8):
+        r = np.arange(-radius, radius + 1)
+        xx, yy = np.meshgrid(r, r)
+        return np.array((xx ** 2 + yy ** 2) <= radius ** 2, dtype=dtype)
+
+    def dilation(image, footprint=None, out=None):
+        return ndimage.grey_dilation(image, footprint=np.asarray(footprint, dtype=bool), mode='constant', cval=0)
+
+    mo.skeletonize, mo.disk, mo.dilation = skeletonize, disk, dilation
+    sk.morphology = mo
+    sys.modules['skimage'], sys.modules['skimage.morphology'] = sk, mo
+
+
 def import_validation(ns):
     """Adds the reference's loss / train / datasets modules (validation path) to `ns`."""
-    import types
-    if 'skimage' not in sys.modules:
-        try:
-            importlib.import_module('skimage.morphology')
-        except ImportError:   # shim 4
-            sk, mo = types.ModuleType('skimage'), types.ModuleType('skimage.morphology')
-
-            def skeletonize(*a, **k):
-                raise RuntimeError('skimage is not installed: the skeleton miners cannot run in this container')
-            mo.skeletonize = skeletonize
-            sk.morphology = mo
-            sys.modules['skimage'], sys.modules['skimage.morphology'] = sk, mo
+    _skimage_shim()
     sys.path.insert(0, str(ns.root))
     try:
         ns.loss = importlib.import_module('src.model.loss')
         ns.train = importlib.import_module('src.train')
         ns.datasets = importlib.import_module('src.utils.datasets')
+    finally:
+        sys.path.remove(str(ns.root))
+    return ns
+
+
+def import_evaluation(ns):
+    """Adds the reference's metrics / evaluation modules to `ns`; numpy >= 2 accepts `np.bool` again."""
+    _skimage_shim()
+    sys.path.insert(0, str(ns.root))
+    try:
+        ns.metrics = importlib.import_module('src.utils.metrics')
+        ns.evaluation = importlib.import_module('src.evaluation')
     finally:
         sys.path.remove(str(ns.root))
     return ns
