@@ -146,6 +146,15 @@ int vosprop_plan_step(int32_t frame_idx, int32_t take_range, int32_t num_refs, f
 /* Introspection for tests / bench. */
 int vosprop_ring_slots(const vosprop_engine* e);
 int vosprop_num_sms(const vosprop_engine* e);
+/* Input normalisation on the device (no engine state): `n` decoded frames, uint8, pixel-interleaved RGB (n, H, W, 3) as a
+ * JPEG decoder leaves them -> (x / 255 - mean[c]) / std[c] in fp32, in the reference's order of operations
+ * (torchvision ToTensor + Normalize, src/utils/datasets.py:128-131, :147), stored as VOSPROP_F32 or VOSPROP_F16 in the same
+ * element order, i.e. an (n, 3, H, W) tensor in channels-last layout -- what the cuDNN backbone consumes.  The fp32
+ * result is bit-identical to the reference's; the fp16 result is that value rounded to nearest, which is what autocast
+ * feeds the first convolution.  Replaces ~7 ms of host arithmetic and a 4x larger host-to-device copy per 480p frame. */
+int vosprop_normalize_u8(const uint8_t* rgb, int64_t n_pixels /* n * H * W */, const float* mean3, const float* std3,
+                         void* out, int32_t out_dtype /* enum vosprop_dtype: F32 or F16 */, void* stream);
+
 /* Work decomposition of the affinity kernel (host arithmetic shared with the device code):
  * fills grid size and per-CTA [begin,end) of the linearised (m_tile, n_tile) space. */
 int vosprop_debug_decompose(int32_t n_pixels, int32_t n_refs, int32_t num_sms, int32_t* grid,

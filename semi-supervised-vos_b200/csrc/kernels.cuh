@@ -727,4 +727,35 @@ __global__ void vos_set_labels_dense(float* __restrict__ meta_slot, const float*
     for (int k = 0; k < kMetaClasses; ++k) rec[k] = (k < d) ? labels[static_cast<size_t>(k) * n_pixels + p] : 0.f;
 }
 
+// -------------------------------------------------------------------------------------------
+// Input normalisation (HBM-bound, caller side of the path): uint8 RGB pixel-interleaved -> (x/255 - mean)/std, same
+// element order (= channels-last NCHW).  fp32 arithmetic in the reference's order (datasets.py:128-131: ToTensor divides
+// by 255, Normalize subtracts the mean, then divides by std); each thread converts 4 pixels (12 bytes in, 3 x 128-bit or
+// 3 x 64-bit out).
+// -------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void vos_normalize_u8(const uint8_t* __restrict__ rgb, T* __restrict__ out, int64_t n_pixels,
+                                 float m0, float m1, float m2, float s0, float s1, float s2) {
+    const int64_t quad = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t p0 = quad * 4;
+    if (p0 >= n_pixels) return;
+    const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+    if (p0 + 4 <= n_pixels) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(rgb + p0 * 3);      // p0 * 3 is a multiple of 12
+        const uint32_t w[3] = {__ldg(src), __ldg(src + 1), __ldg(src + 2)};
+        T v[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            const float x = static_cast<float>((w[i >> 2] >> (8 * (i & 3))) & 0xffu);
+            v[i] = static_cast<T>(__fdiv_rn(__fdiv_rn(x, 255.f) - mean[i % 3], sd[i % 3]));
+        }
+        T* dst = out + p0 * 3;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) dst[i] = v[i];       // 48 / 24 contiguous bytes per thread: the compiler vectorises
+    } else {
+        for (int64_t i = p0 * 3; i < n_pixels * 3; ++i)
+            out[i] = static_cast<T>(__fdiv_rn(__fdiv_rn(static_cast<float>(rgb[i]), 255.f) - mean[i % 3], sd[i % 3]));
+    }
+}
+
 }  // namespace vosk

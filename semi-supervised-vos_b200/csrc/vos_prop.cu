@@ -565,6 +565,28 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     return VOSPROP_OK;
 }
 
+int vosprop_normalize_u8(const uint8_t* rgb, int64_t n_pixels, const float* mean3, const float* std3, void* out,
+                         int32_t out_dtype, void* stream) {
+    if (!rgb || !out || !mean3 || !std3) return fail(VOSPROP_ERR_INVALID, "null pointer");
+    if (n_pixels < 0) return fail(VOSPROP_ERR_INVALID, "negative pixel count");
+    if (out_dtype != VOSPROP_F32 && out_dtype != VOSPROP_F16) return fail(VOSPROP_ERR_INVALID, "output dtype %d: F32 or F16", out_dtype);
+    if ((reinterpret_cast<uintptr_t>(rgb) & 3) || (reinterpret_cast<uintptr_t>(out) & 15))
+        return fail(VOSPROP_ERR_INVALID, "normalize: input must be 4-byte and output 16-byte aligned");
+    if (n_pixels == 0) return VOSPROP_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int threads = 256;
+    const int64_t quads = (n_pixels + 3) / 4;
+    const unsigned blocks = static_cast<unsigned>((quads + threads - 1) / threads);
+    if (out_dtype == VOSPROP_F32)
+        vosk::vos_normalize_u8<float><<<blocks, threads, 0, st>>>(rgb, static_cast<float*>(out), n_pixels, mean3[0], mean3[1], mean3[2],
+                                                                  std3[0], std3[1], std3[2]);
+    else
+        vosk::vos_normalize_u8<__half><<<blocks, threads, 0, st>>>(rgb, static_cast<__half*>(out), n_pixels, mean3[0], mean3[1], mean3[2],
+                                                                   std3[0], std3[1], std3[2]);
+    VOS_CUDA(cudaGetLastError());
+    return VOSPROP_OK;
+}
+
 int vosprop_sample_frames(int32_t frame_idx, int32_t take_range, int32_t num_refs, int32_t* out_idx) {
     // src/model/predict.py:74-89
     if (!out_idx) return fail(VOSPROP_ERR_INVALID, "null out_idx");

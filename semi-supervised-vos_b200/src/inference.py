@@ -50,8 +50,15 @@ def inference_command(ref_num, data, resume, model, temperature, frame_range, si
 
 
 def _load_net(arch, checkpoint):
-    net = load_model(VOSNet(model=arch), checkpoint)
-    return net.to(Config.DEVICE).eval()
+    """Checkpoint -> eval-mode network on Config.DEVICE.  The ImageNet initialisation the reference downloads first
+    (vos_net.py:17-19) is overwritten by the checkpoint anyway and is skipped.  ResNet trunks run in their cuDNN-fused
+    inference form (BatchNorm folded, bias / ReLU / residual in the convolution epilogue, fp16 as under the reference's
+    autocast); VOS_FUSE_BACKBONE=0 keeps the plain module."""
+    net = load_model(VOSNet(model=arch, pretrained=False), checkpoint).to(Config.DEVICE).eval()
+    if Config.DEVICE.type == 'cuda' and arch in ('resnet18', 'resnet50', 'resnet101') and os.environ.get('VOS_FUSE_BACKBONE', '1') != '0':
+        from vosb200.fused_backbone import FusedVOSNet
+        return FusedVOSNet(net)
+    return net
 
 
 def inference_command_impl(ref_num, data, resume, model, temperature, frame_range, sigma_1, sigma_2, save, device,
@@ -63,7 +70,7 @@ def inference_command_impl(ref_num, data, resume, model, temperature, frame_rang
     additional_model = _load_net(additional_model_type, additional_resume) if inference_strategy == 'multimodel' else None
 
     dataset = InferenceDataset(str(Path(data) / 'JPEGImages/480p'), disable=disable,
-                               inference_strategy=inference_strategy, scale=scale)
+                               inference_strategy=inference_strategy, scale=scale, raw=True)
     # the reference decodes with one worker (inference.py:75-78); JPEG decode is the slowest stage once propagation runs on
     # the GPU, so it is spread over workers here (same PIL decode, same order: shuffle=False)
     loader = torch.utils.data.DataLoader(dataset, batch_size=1, shuffle=False, num_workers=min(8, os.cpu_count() or 1),

@@ -61,9 +61,14 @@ class TrainDataset(datasets.ImageFolder):
 
 
 class InferenceDataset(datasets.ImageFolder):
+    """`raw=True` (what `inference_command_impl` asks for): items carry the decoded frame as a uint8 (H,W,3) tensor instead
+    of the normalised fp32 (3,H,W) one; the loops normalise it on the GPU (vosprop_normalize_u8: same arithmetic, same
+    bits) -- ToTensor + Normalize cost more host time per 480p frame than the JPEG decode."""
+
     def __init__(self, root, transform=None, target_transform=None, disable=False,
-                 inference_strategy='single', scale=None):
+                 inference_strategy='single', scale=None, raw=False):
         super().__init__(root, transform=transform, target_transform=target_transform)
+        self.raw = raw
         self.rgb_normalize = transforms.Compose([
             transforms.ToTensor(),
             transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
@@ -78,16 +83,17 @@ class InferenceDataset(datasets.ImageFolder):
         _, video_index = self.imgs[index]
         img = Image.open(BytesIO(self.img_bytes[index])).convert('RGB')
         # the reference resizes to ceil(size) == size with ANTIALIAS: an identity resample
-        normalized = self.rgb_normalize(np.asarray(img))
+        tensor = (lambda im: torch.from_numpy(np.array(im))) if self.raw else (lambda im: self.rgb_normalize(np.asarray(im)))
+        normalized = tensor(img)
         video = self.idx_to_class[video_index]
         if self.inference_strategy == 'hor-flip':
-            return (normalized, self.rgb_normalize(np.asarray(ImageOps.mirror(img)))), video
+            return (normalized, tensor(ImageOps.mirror(img))), video
         if self.inference_strategy == 'vert-flip':
-            return (normalized, self.rgb_normalize(np.asarray(ImageOps.flip(img)))), video
+            return (normalized, tensor(ImageOps.flip(img))), video
         if self.inference_strategy in ('2-scale', 'hor-2-scale'):
             size2 = tuple(int(v) for v in np.ceil(np.array(img.size) * self.scale))
             src = ImageOps.mirror(img) if self.inference_strategy == 'hor-2-scale' else img
-            return (normalized, self.rgb_normalize(np.asarray(src.resize(size2, Image.LANCZOS)))), video
+            return (normalized, tensor(src.resize(size2, Image.LANCZOS))), video
         return normalized, video
 
     def __len__(self):

@@ -16,7 +16,7 @@ from tqdm import tqdm
 from src.config import Config
 from src.model.predict import prepare_first_frame
 from src.utils.utils import save_predictions
-from vosb200 import PropagationEngine
+from vosb200 import PropagationEngine, normalize_frames
 from vosb200.engine import precision_for, required_ring_slots
 from vosb200.sequence import nearest_index
 
@@ -27,11 +27,16 @@ REDUCTIONS = {'maximum': lambda x, y: torch.maximum(x, y),
 _ENGINES = {}
 
 
-def _engine_for(n_pixels: int, slots: int) -> PropagationEngine:
+def _require_cuda() -> torch.device:
     dev = torch.device(Config.DEVICE)
     if dev.type != 'cuda':
         raise RuntimeError("this build runs the propagation on a B200 only: use --device cuda "
                            "(there is no CPU path; the CPU reference lives in oracle/ for tests)")
+    return dev
+
+
+def _engine_for(n_pixels: int, slots: int) -> PropagationEngine:
+    dev = _require_cuda()
     key = (dev.index or 0,)
     eng = _ENGINES.get(key)
     if eng is None or eng.max_pixels < n_pixels or eng.ring_slots < slots:
@@ -115,6 +120,60 @@ class _PngWriter:
 _WRITER = _PngWriter()
 
 
+def _to_device(input):
+    """Loader item -> network input on Config.DEVICE: the reference's normalised fp32 (n,3,H,W) tensor as is, or decoded
+    uint8 (n,H,W,3) frames (InferenceDataset(raw=True)) normalised on the GPU -- bit-identical values, a quarter of the
+    bytes over PCIe."""
+    input = input.to(_require_cuda(), non_blocking=True)
+    if input.dtype == torch.uint8:
+        return normalize_frames(input, torch.float32)
+    return input
+
+
+BACKBONE_LOOKAHEAD = 8     # frames of one video embedded per backbone call (a batch-1 ResNet is launch-bound on a B200)
+
+
+def _embedded(models, inference_loader, total_len, disable, resize=None, shared_input=False):
+    """Frame-by-frame view of the loader with the backbone run on up to BACKBONE_LOOKAHEAD consecutive frames of one
+    video at a time.  Feature extraction does not depend on the propagation state (the reference calls model(input) on
+    every frame independently, inference_utils.py:35,52), so only the launch count changes.
+    `models`: one network -> yields (features (1,K,H_d,W_d), (H, W) of the network input, video name); a tuple of
+    networks, one per stream of a test-time-augmentation strategy (loader items carry one input per stream, or a single
+    input for all of them with shared_input) -> yields (tuple of features, tuple of sizes, video name).
+    `resize`: optional (H, W) -> (H', W') applied with nearest interpolation before the network (3-scale)."""
+    single = not isinstance(models, (tuple, list))
+    nets = (models,) if single else tuple(models)
+    pending = []
+
+    def flush():
+        feats, sizes = [], []
+        for k, net in enumerate(nets):
+            if k and shared_input:
+                x = xs
+            else:
+                x = xs = _to_device(torch.cat([inputs[0 if shared_input else k] for inputs, _ in pending]))
+                if resize is not None:
+                    x = xs = torch.nn.functional.interpolate(x, size=resize(x.shape[2], x.shape[3]), mode='nearest')
+            with torch.autocast('cuda', dtype=torch.float16):
+                feats.append(net(x))
+            sizes.append((x.shape[2], x.shape[3]))
+        for i, (_, video) in enumerate(pending):
+            if single:
+                yield feats[0][i:i + 1], sizes[0], video
+            else:
+                yield tuple(f[i:i + 1] for f in feats), tuple(sizes), video
+        pending.clear()
+
+    for input, (current_video,) in tqdm(inference_loader, total=total_len, disable=disable):
+        inputs = (input,) if (single or shared_input) else tuple(input)
+        if pending and (current_video != pending[0][1] or any(a.shape != b.shape for a, b in zip(inputs, pending[0][0]))
+                        or len(pending) == BACKBONE_LOOKAHEAD):
+            yield from flush()
+        pending.append((inputs, current_video))
+    if pending:
+        yield from flush()
+
+
 def inference_single(model, inference_loader, total_len, annotation_dir, last_video, save, sigma_1, sigma_2,
                      frame_range, ref_num, temperature, probability_propagation, disable):
     """Reference: src/utils/inference_utils.py:23-87."""
@@ -122,21 +181,17 @@ def inference_single(model, inference_loader, total_len, annotation_dir, last_vi
     sink = None
     engine = None
     slots = required_ring_slots(frame_range, ref_num)
-    for input, (current_video,) in tqdm(inference_loader, total=total_len, disable=disable):
+    for features, (H, W), current_video in _embedded(model, inference_loader, total_len, disable):
         if current_video != last_video:
             if sink is not None:
                 sink.flush()
                 sink = None
             frame_idx = 0
-        input = input.to(Config.DEVICE, non_blocking=True)
-        with torch.autocast('cuda', dtype=torch.float16):
-            features = model(input)
         if frame_idx == 0:
             first_annotation = annotation_dir / current_video / '00000.png'
             label_1hot, d, palette, _, _ = prepare_first_frame(
                 current_video, save, first_annotation, sigma_1, sigma_2, inference_strategy='single',
                 probability_propagation=probability_propagation)
-            (_, _, H, W) = input.shape
             (_, _, H_d, W_d) = features.shape
             engine = _engine_for(H_d * W_d, slots)
             engine.reset(H_d, W_d, H, W, int(d), precision_for(features.dtype))   # fp16 under autocast -> one exact pass
@@ -210,18 +265,13 @@ def _inference_two_streams(models, inference_loader, total_len, annotation_dir, 
     slots = required_ring_slots(frame_range, ref_num)
     a, b = _Stream(slots), _Stream(slots)
     frame_idx, sink = 0, None
-    for input, (current_video,) in tqdm(inference_loader, total=total_len, disable=disable):
+    for (features_a, features_b), ((H, W), _), current_video in _embedded(models, inference_loader, total_len, disable,
+                                                                       shared_input=strategy == 'multimodel'):
         if current_video != last_video:
             if sink is not None:
                 sink.flush()
                 sink = None
             frame_idx = 0
-        if strategy == 'multimodel':
-            input_a = input_b = input.to(Config.DEVICE, non_blocking=True)
-        else:
-            input_a, input_b = input[0].to(Config.DEVICE, non_blocking=True), input[1].to(Config.DEVICE, non_blocking=True)
-        with torch.autocast('cuda', dtype=torch.float16):
-            features_a, features_b = models[0](input_a), models[1](input_b)
         if frame_idx == 0:
             first_annotation = annotation_dir / current_video / '00000.png'
             prepared = prepare_first_frame(current_video, save, first_annotation, sigma_1, sigma_2,
@@ -234,7 +284,6 @@ def _inference_two_streams(models, inference_loader, total_len, annotation_dir, 
             else:   # multimodel: one label set for both models
                 label_a = label_b = prepared[0]
                 d, palette = prepared[1], prepared[2]
-            (_, _, H, W) = input_a.shape
             a.start(features_a, label_a, H, W, d)
             b.start(features_b, label_b, H, W, d)     # both memories predict at the size of the first input
             sink = _VideoSink(current_video, palette, save, H, W, features_a.device)
@@ -312,16 +361,12 @@ def inference_3_scale(model, inference_loader, total_len, annotation_dir, last_v
             if k == len(scales) - 1:
                 sink.flush(fused.pop(sink.video))
 
-        for input, (current_video,) in tqdm(inference_loader, total=total_len, disable=disable):
-            (_, _, H, W) = input.shape
-            size = (int(np.ceil(H * s)), int(np.ceil(W * s)))
-            input = torch.nn.functional.interpolate(input.to(Config.DEVICE, non_blocking=True), size=size, mode='nearest')
+        resize = lambda H, W, s=s: (int(np.ceil(H * s)), int(np.ceil(W * s)))      # noqa: E731
+        for features, size, current_video in _embedded(model, inference_loader, total_len, disable, resize=resize):
             if current is not None and current_video != current:
                 finish(sink)
                 frame_idx = 0
             current = current_video
-            with torch.autocast('cuda', dtype=torch.float16):
-                features = model(input)
             if frame_idx == 0:
                 first_annotation = annotation_dir / current_video / '00000.png'
                 label_1hot, d, palette, _, _ = prepare_first_frame(

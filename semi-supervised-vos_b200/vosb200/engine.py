@@ -48,6 +48,27 @@ def precision_for(dtype: torch.dtype) -> int:
     return {torch.float16: capi.PREC_F16, torch.bfloat16: capi.PREC_BF16}.get(dtype, capi.PREC_SPLIT3)
 
 
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)     # src/utils/datasets.py:128-131
+
+
+def normalize_frames(rgb: torch.Tensor, dtype: torch.dtype = torch.float16, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> torch.Tensor:
+    """Decoded frames (n,H,W,3) uint8 on the GPU -> (n,3,H,W) normalised tensor in channels-last layout (the element
+    order does not change), fp32 (bit-identical to torchvision's ToTensor + Normalize) or fp16 (that value rounded)."""
+    if rgb.dtype != torch.uint8 or not rgb.is_cuda or rgb.dim() != 4 or rgb.shape[3] != 3:
+        raise TypeError(f'expected a CUDA uint8 (n,H,W,3) tensor, got {rgb.dtype} {tuple(rgb.shape)} on {rgb.device}')
+    if dtype not in (torch.float32, torch.float16):
+        raise TypeError('normalize_frames writes fp32 or fp16')
+    rgb = rgb.contiguous()
+    n, H, W, _ = rgb.shape
+    out = torch.empty((n, 3, H, W), dtype=dtype, device=rgb.device, memory_format=torch.channels_last)
+    m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    with torch.cuda.device(rgb.device):
+        capi.check(capi.lib().vosprop_normalize_u8(C.c_void_p(rgb.data_ptr()), n * H * W, m3, s3, C.c_void_p(out.data_ptr()),
+                                                    _DTYPES[dtype], C.c_void_p(torch.cuda.current_stream(rgb.device).cuda_stream)))
+    rgb.record_stream(torch.cuda.current_stream(rgb.device))
+    return out
+
+
 def required_ring_slots(frame_range: int, ref_num: int) -> int:
     """Slots needed so that every frame sample_frames can pick is still resident, plus the target."""
     return max(frame_range + CONTINUOUS_FRAME, ref_num) + 1

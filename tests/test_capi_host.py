@@ -25,7 +25,7 @@ def lib():
 def test_exports_every_declared_symbol(lib):
     from vosb200 import _capi
     header = (REPO / 'include' / 'vos_prop.h').read_text()
-    declared = set(re.findall(r'\b(vosprop_[a-z_]+)\s*\(', header))
+    declared = set(re.findall(r'\b(vosprop_[a-z0-9_]+)\s*\(', header))
     assert declared, 'no declarations parsed'
     assert declared == set(_capi.EXPORTS), declared ^ set(_capi.EXPORTS)
     for name in declared:

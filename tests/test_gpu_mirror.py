@@ -27,7 +27,8 @@ def _read_masks(save, video, T):
 
 
 def _table(feats):
-    return lambda inp: feats[int(inp[0, 0, 0, 0].item())][None]
+    """'Network' that looks the embedding of every frame of the batch up by the frame number encoded in the input."""
+    return lambda inp: torch.stack([feats[int(v)] for v in inp[:, 0, 0, 0].tolist()])
 
 
 @pytest.fixture()
@@ -74,7 +75,7 @@ def test_two_stream_strategies_write_the_reference_pngs(name, tmp_path, mirror):
         else:
             loader = [([torch.full((1, 1, H, W), float(t)), torch.full((1, 1, Hb, Wb), float(t) + 0.25)], ('clip',))
                       for t in range(T)]
-            model = lambda inp: (fb if float(inp[0, 0, 0, 0]) % 1 else fa)[int(inp[0, 0, 0, 0].item())][None]  # noqa: E731
+            model = lambda inp: torch.stack([(fb if v % 1 else fa)[int(v)] for v in inp[:, 0, 0, 0].tolist()])  # noqa: E731
             if strategy == 'hor-flip':
                 mirror.inference_hor_flip(model, loader, *common, cfg['reduction'], True)
             elif strategy == 'vert-flip':
@@ -115,8 +116,8 @@ def test_three_scale_writes_the_reference_pngs(name, tmp_path, mirror):
     ann_dir, save = tmp_path / 'Annotations' / '480p', tmp_path / 'out'
 
     def model(inp):
-        code = int(inp[0, 0, 0, 0].item())
-        return feats[videos[code // 1000]][by_shape[tuple(inp.shape[2:])]][code % 1000][None]
+        k = by_shape[tuple(inp.shape[2:])]
+        return torch.stack([feats[videos[int(c) // 1000]][k][int(c) % 1000] for c in inp[:, 0, 0, 0].tolist()])
 
     loader = [(torch.full((1, 1, H, W), float(1000 * vi + t)), (v['name'],)) for vi, v in enumerate(cfg['videos'])
               for t in range(v['T'])]

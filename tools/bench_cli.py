@@ -39,7 +39,7 @@ def make_dataset(root, videos=4, frames=50, H=480, W=854, seed=0):
 def main():
     from src.inference import inference_command_impl
     from src.model.vos_net import VOSNet
-    videos, frames = 4, 50
+    videos, frames = 8, 100
     with tempfile.TemporaryDirectory() as tmp:
         root = Path(tmp)
         make_dataset(root, videos, frames)
