@@ -73,7 +73,8 @@ def inference_command_impl(ref_num, data, resume, model, temperature, frame_rang
                                inference_strategy=inference_strategy, scale=scale, raw=True)
     # the reference decodes with one worker (inference.py:75-78); JPEG decode is the slowest stage once propagation runs on
     # the GPU, so it is spread over workers here (same PIL decode, same order: shuffle=False)
-    loader = torch.utils.data.DataLoader(dataset, batch_size=1, shuffle=False, num_workers=min(8, os.cpu_count() or 1),
+    cpus = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    loader = torch.utils.data.DataLoader(dataset, batch_size=1, shuffle=False, num_workers=max(1, min(12, cpus - 4, cpus)) if cpus > 8 else min(8, cpus),
                                          pin_memory=True, prefetch_factor=4, persistent_workers=False)
     annotation_dir = Path(data) / 'Annotations/480p'
     last_video = sorted(annotation_dir.glob('*'))[0].name

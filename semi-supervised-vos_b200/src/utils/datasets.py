@@ -81,7 +81,9 @@ class InferenceDataset(datasets.ImageFolder):
 
     def __getitem__(self, index):
         _, video_index = self.imgs[index]
-        img = Image.open(BytesIO(self.img_bytes[index])).convert('RGB')
+        img = Image.open(BytesIO(self.img_bytes[index]))
+        if img.mode != 'RGB':                      # convert() copies even when there is nothing to convert (1.6 ms at 480p)
+            img = img.convert('RGB')
         # the reference resizes to ceil(size) == size with ANTIALIAS: an identity resample
         tensor = (lambda im: torch.from_numpy(np.array(im))) if self.raw else (lambda im: self.rgb_normalize(np.asarray(im)))
         normalized = tensor(img)

@@ -15,7 +15,7 @@ from tqdm import tqdm
 
 from src.config import Config
 from src.model.predict import prepare_first_frame
-from src.utils.utils import save_predictions
+from src.utils.utils import save_prediction
 from vosb200 import PropagationEngine, normalize_frames
 from vosb200.engine import precision_for, required_ring_slots
 from vosb200.sequence import nearest_index
@@ -80,10 +80,12 @@ class _VideoSink:
 
 
 class _PngWriter:
-    """Background writer of finished videos (bounded: at most two videos wait for their files)."""
+    """Background writer of finished videos (bounded: at most two videos wait for their files).  One dispatcher thread
+    waits for a video's D2H copy and fans its frames out to a small pool: PIL's PNG encoder releases the GIL, and a
+    single encoder (about 2-5 ms per 480p mask) would otherwise cap the whole command below 500 frames/s."""
 
     def __init__(self):
-        self._queue, self._thread = None, None
+        self._queue, self._thread, self._pool, self._error = None, None, None, None
 
     def _run(self):
         while True:
@@ -93,17 +95,24 @@ class _PngWriter:
                     return
                 done, host, palette, save, video = item
                 done.synchronize()
-                save_predictions(host.numpy(), palette, save, video)
+                masks = host.numpy()
+                # frames 1..T-1 -> 00001.png ... exactly as save_predictions (utils.py:97-100), several files at a time
+                list(self._pool.map(lambda job: save_prediction(job[1], palette, save, str(job[0]).zfill(5), video),
+                                    enumerate(masks, start=1)))
             except BaseException as exc:  # noqa: BLE001 - surfaced by drain()
                 self._error = exc
             finally:
                 self._queue.task_done()
 
     def submit(self, *item):
+        import os
         import queue
         import threading
+        from concurrent.futures import ThreadPoolExecutor
         if self._thread is None or not self._thread.is_alive():
+            cpus = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
             self._queue, self._error = queue.Queue(maxsize=2), None
+            self._pool = ThreadPoolExecutor(max_workers=max(1, min(6, cpus // 2)), thread_name_prefix='vos-png')
             self._thread = threading.Thread(target=self._run, name='vos-png-writer', daemon=True)
             self._thread.start()
         self._queue.put(item)
