@@ -149,20 +149,21 @@ def _embedded(models, inference_loader, total_len, disable, resize=None, shared_
     `models`: one network -> yields (features (1,K,H_d,W_d), (H, W) of the network input, video name); a tuple of
     networks, one per stream of a test-time-augmentation strategy (loader items carry one input per stream, or a single
     input for all of them with shared_input) -> yields (tuple of features, tuple of sizes, video name).
-    `resize`: optional (H, W) -> (H', W') applied with nearest interpolation before the network (3-scale)."""
+    `resize`: optional (H, W) -> (H', W'), or one per stream, applied with nearest interpolation before the network
+    (3-scale)."""
     single = not isinstance(models, (tuple, list))
     nets = (models,) if single else tuple(models)
     pending = []
 
     def flush():
         feats, sizes = [], []
+        base = None
         for k, net in enumerate(nets):
-            if k and shared_input:
-                x = xs
-            else:
-                x = xs = _to_device(torch.cat([inputs[0 if shared_input else k] for inputs, _ in pending]))
-                if resize is not None:
-                    x = xs = torch.nn.functional.interpolate(x, size=resize(x.shape[2], x.shape[3]), mode='nearest')
+            if base is None or not shared_input:
+                base = _to_device(torch.cat([inputs[0 if shared_input else k] for inputs, _ in pending]))
+            x, r = base, (resize[k] if isinstance(resize, (tuple, list)) else resize)
+            if r is not None:
+                x = torch.nn.functional.interpolate(base, size=r(base.shape[2], base.shape[3]), mode='nearest')
             with torch.autocast('cuda', dtype=torch.float16):
                 feats.append(net(x))
             sizes.append((x.shape[2], x.shape[3]))
@@ -246,13 +247,14 @@ class _Stream:
         self.engine.append(0, features)
         self.engine.set_labels_index(0, label_1hot[:, 0].argmax(0))
 
-    def step(self, frame_idx, features, p, probability_propagation):
-        """-> (H,W) uint8 label map, or the (1,d,H,W) fp32 up-sampled prediction in probability mode."""
+    def step(self, frame_idx, features, p, probability_propagation, want_mask=False):
+        """-> (H,W) uint8 label map, or (unless want_mask) the (1,d,H,W) fp32 up-sampled prediction in probability mode."""
         self.engine.append(frame_idx, features)
+        want_mask = want_mask or not probability_propagation
         out = self.engine.step(frame_idx, p['frame_range'], p['ref_num'], p['sigma_1'], p['sigma_2'], p['temperature'],
-                               probability_propagation, want_prediction=probability_propagation, want_lowres=False,
-                               want_fullres=not probability_propagation)
-        if not probability_propagation:
+                               probability_propagation, want_prediction=not want_mask, want_lowres=False,
+                               want_fullres=want_mask)
+        if want_mask:
             return out['mask']
         H_d, W_d, H, W, d = self.geom
         ys, xs = nearest_index(H, H_d, features.device), nearest_index(W, W_d, features.device)
@@ -352,51 +354,42 @@ THREE_SCALE_OUT = (480, 910)     # the reference up-samples every scale's predic
 
 def inference_3_scale(model, inference_loader, total_len, annotation_dir, last_video, save, sigma_1, sigma_2,
                       frame_range, ref_num, temperature, probability_propagation, scale, disable):
-    """Reference: src/utils/inference_utils.py:514-595.  Three passes over the loader with the frames nearest-resized
-    by 0.9 / 1.0 / `scale`; each pass is a plain single-memory propagation whose label maps are written at 480 x 910
-    (hard-coded there, :574; kept, because the drop-in must write the files the reference writes); the three label maps
-    of a frame are fused by an element-wise maximum of the class indices (:594).  The running maximum stays on the
-    device; a video's PNGs are queued as soon as its third pass ends."""
+    """Reference: src/utils/inference_utils.py:514-595: the frames nearest-resized by 0.9 / 1.0 / `scale`, one plain
+    single-memory propagation per scale, every label map written at 480 x 910 (hard-coded there, :574; kept, because the
+    drop-in must write the files the reference writes), the three maps of a frame fused by an element-wise maximum of the
+    class indices (:594).  The reference runs the loader three times, one pass per scale; the three propagations never
+    exchange anything, so here they run side by side on one pass (three memories, one JPEG decode per frame) and the
+    fused map goes straight to the video's sink."""
     H_out, W_out = THREE_SCALE_OUT
+    p = dict(sigma_1=sigma_1, sigma_2=sigma_2, frame_range=frame_range, ref_num=ref_num, temperature=temperature)
     slots = required_ring_slots(frame_range, ref_num)
-    fused, palettes = {}, {}
     scales = (0.9, 1.0, scale)
-    for k, s in enumerate(scales):
-        frame_idx, sink, engine, current = 0, None, None, None
-
-        def finish(sink):
-            masks = sink.stacked()
-            fused[sink.video] = masks if k == 0 else torch.maximum(fused[sink.video], masks)
-            if k == len(scales) - 1:
-                sink.flush(fused.pop(sink.video))
-
-        resize = lambda H, W, s=s: (int(np.ceil(H * s)), int(np.ceil(W * s)))      # noqa: E731
-        for features, size, current_video in _embedded(model, inference_loader, total_len, disable, resize=resize):
-            if current is not None and current_video != current:
-                finish(sink)
-                frame_idx = 0
-            current = current_video
-            if frame_idx == 0:
-                first_annotation = annotation_dir / current_video / '00000.png'
+    streams = [_Stream(slots) for _ in scales]
+    resize = [lambda H, W, s=s: (int(np.ceil(H * s)), int(np.ceil(W * s))) for s in scales]
+    frame_idx, sink, current = 0, None, None
+    for features, sizes, current_video in _embedded((model,) * len(scales), inference_loader, total_len, disable,
+                                                    resize=resize, shared_input=True):
+        if current is not None and current_video != current:
+            sink.flush()
+            frame_idx = 0
+        current = current_video
+        if frame_idx == 0:
+            first_annotation = annotation_dir / current_video / '00000.png'
+            for k, s in enumerate(scales):
                 label_1hot, d, palette, _, _ = prepare_first_frame(
                     current_video, save, first_annotation, sigma_1, sigma_2, inference_strategy='3-scale',
                     probability_propagation=probability_propagation, scale=s)
-                (_, _, H_d, W_d) = features.shape
+                (_, _, H_d, W_d) = features[k].shape
                 if label_1hot.shape[-1] != H_d * W_d:
-                    raise ValueError(f'scale {s}: the network maps {size} to {(H_d, W_d)} but the annotation is sampled '
+                    raise ValueError(f'scale {s}: the network maps {sizes[k]} to {(H_d, W_d)} but the annotation is sampled '
                                      f'at {label_1hot.shape[-1]} pixels (the reference fails on such sizes too)')
-                engine = _engine_for(H_d * W_d, slots)
-                engine.reset(H_d, W_d, H_out, W_out, int(d), precision_for(features.dtype))
-                engine.append(0, features)
-                engine.set_labels_index(0, label_1hot[:, 0].argmax(0))
-                palettes.setdefault(current_video, palette)
-                sink = _VideoSink(current_video, palettes[current_video], save, H_out, W_out, features.device)
-                frame_idx += 1
-                continue
-            engine.append(frame_idx, features)
-            engine.step(frame_idx, frame_range, ref_num, sigma_1, sigma_2, temperature, probability_propagation,
-                        want_prediction=False, want_lowres=False, want_fullres=False, out_fullres=sink.next_slot())
+                streams[k].start(features[k], label_1hot, H_out, W_out, d)
+            sink = _VideoSink(current_video, palette, save, H_out, W_out, features[0].device)
             frame_idx += 1
-        if sink is not None:
-            finish(sink)
+            continue
+        masks = [st.step(frame_idx, features[k], p, probability_propagation, want_mask=True) for k, st in enumerate(streams)]
+        sink.next_slot().copy_(torch.maximum(torch.maximum(masks[0], masks[1]), masks[2]))
+        frame_idx += 1
+    if sink is not None:
+        sink.flush()
     _WRITER.drain()
