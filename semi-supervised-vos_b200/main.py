@@ -2,19 +2,11 @@
 next to the propagation hot path are registered: `inference`, `validation` and `evaluation` (`train` is out of scope)."""
 import click
 
-from src.evaluation import evaluation_command
-from src.inference import inference_command
-from src.validation import validation_command
+from src import evaluation, inference, validation
 
-
-@click.group(name='cli')
-def cli():
-    pass
-
-
-cli.add_command(inference_command)
-cli.add_command(validation_command)
-cli.add_command(evaluation_command)
+cli = click.Group(name='cli', commands={cmd.name: cmd for cmd in (inference.inference_command,
+                                                                 validation.validation_command,
+                                                                 evaluation.evaluation_command)})
 
 if __name__ == '__main__':
     cli()
