@@ -516,31 +516,65 @@ template <int kCap>   // class capacity of this instantiation: kMetaClasses (the
 __global__ void __launch_bounds__(kMergeThreads) vos_merge_writeback(const MergeParams prm) {
     extern __shared__ uint8_t row_cls[];  // [w_lowres]
     pdl_launch_dependents();
-    pdl_wait();                           // the affinity kernel's partials (and everything before it) are complete
     const int y = blockIdx.x;
     const int sublane = threadIdx.x & (kMergeLanes - 1);
     const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~(kMergeLanes - 1));   // the 8 lanes of this pixel group
     const int32_t* mt0 = prm.tables + 2 * prm.tpf;
+    const int sub_shift = prm.n_sub == 4 ? 2 : 1;        // n_sub is 2 (general kernel) or 4 (index-label kernel)
+    constexpr int kMaxRec = 4;                           // records a lane folds without looping (8 lanes x 4 = 32 per pixel)
+    bool waited = false;
     for (int x = threadIdx.x / kMergeLanes; x < prm.w_lowres; x += kMergeThreads / kMergeLanes) {
         const int pix = y * prm.w_lowres + x;
         const int mt = pix / kTile, row = pix % kTile;
+        // Everything up to here depends only on the decomposition tables (written by an earlier kernel of the stream):
+        // it runs while the affinity kernel before us is still executing; the partials are touched after pdl_wait().
         const int c_first = prm.tables[mt], c_last = prm.tables[prm.tpf + mt];
-        const int n_rec = (c_last - c_first + 1) * prm.n_sub;
-        // each lane folds records sublane, sublane+8, ... (online softmax merge), then an 8-lane butterfly
+        const int n_rec = (c_last - c_first + 1) << sub_shift;
+        const float* recs[kMaxRec];
+#pragma unroll
+        for (int j = 0; j < kMaxRec; ++j) {
+            const int i = sublane + j * kMergeLanes;
+            recs[j] = nullptr;
+            if (i < n_rec) {
+                const int c = c_first + (i >> sub_shift), h = i & (prm.n_sub - 1);
+                recs[j] = prm.partials + (static_cast<size_t>(c * prm.max_segs + (mt - mt0[c])) * prm.n_sub + h) * kPartFloats + row;
+            }
+        }
+        if (!waited) {
+            pdl_wait();                   // the affinity kernel's partials (and everything before it) are complete
+            waited = true;
+        }
+        // two passes over this lane's records: the maximum first, then the weighted sums -- every load is independent of
+        // the arithmetic on the previous record
         float M = kNegBig, L = 0.f, acc[kCap];
 #pragma unroll
         for (int k = 0; k < kCap; ++k) acc[k] = 0.f;
-        for (int i = sublane; i < n_rec; i += kMergeLanes) {
-            const int c = c_first + i / prm.n_sub, h = i % prm.n_sub;
-            const int seg = mt - mt0[c];
-            const float* rec = prm.partials + (static_cast<size_t>(c * prm.max_segs + seg) * prm.n_sub + h) * kPartFloats;
-            const float m_r = rec[row];
-            const float M_new = fmaxf(M, m_r);
-            const float w_old = vosptx::ex2(M - M_new), w_new = vosptx::ex2(m_r - M_new);
-            L = fmaf(rec[kTile + row], w_new, L * w_old);
+        float m_r[kMaxRec];
+#pragma unroll
+        for (int j = 0; j < kMaxRec; ++j) {
+            m_r[j] = recs[j] ? recs[j][0] : kNegBig;
+            M = fmaxf(M, m_r[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < kMaxRec; ++j) {
+            if (recs[j]) {
+                const float w = vosptx::ex2(m_r[j] - M);
+                L = fmaf(recs[j][kTile], w, L);
+#pragma unroll
+                for (int k = 0; k < kCap; ++k)
+                    if (k < prm.d) acc[k] = fmaf(recs[j][(2 + k) * kTile], w, acc[k]);
+            }
+        }
+        for (int i = sublane + kMaxRec * kMergeLanes; i < n_rec; i += kMergeLanes) {      // (very long segment lists only)
+            const int c = c_first + (i >> sub_shift), h = i & (prm.n_sub - 1);
+            const float* rec = prm.partials + (static_cast<size_t>(c * prm.max_segs + (mt - mt0[c])) * prm.n_sub + h) * kPartFloats + row;
+            const float mr = rec[0];
+            const float M_new = fmaxf(M, mr);
+            const float w_old = vosptx::ex2(M - M_new), w_new = vosptx::ex2(mr - M_new);
+            L = fmaf(rec[kTile], w_new, L * w_old);
 #pragma unroll
             for (int k = 0; k < kCap; ++k)
-                if (k < prm.d) acc[k] = fmaf(rec[(2 + k) * kTile + row], w_new, acc[k] * w_old);
+                if (k < prm.d) acc[k] = fmaf(rec[(2 + k) * kTile], w_new, acc[k] * w_old);
             M = M_new;
         }
 #pragma unroll
@@ -579,14 +613,14 @@ __global__ void __launch_bounds__(kMergeThreads) vos_merge_writeback(const Merge
         if (prm.out_mask_lowres) prm.out_mask_lowres[pix] = static_cast<uint8_t>(best);
         row_cls[x] = static_cast<uint8_t>(best);
     }
+    if (!waited) pdl_wait();
     if (!prm.out_mask_fullres) return;
     __syncthreads();
     const float sy = static_cast<float>(prm.h_lowres) / static_cast<float>(prm.H);
     const float sx = static_cast<float>(prm.w_lowres) / static_cast<float>(prm.W);
     // full-res rows that sample low-res row y: a window around y/sy, filtered by the exact rule
-    const int guess = static_cast<int>(static_cast<float>(y) / sy);
-    const int span = static_cast<int>(1.0f / sy) + 2;
-    const int dy0 = max(0, guess - span), dy1 = min(prm.H, guess + 2 * span);
+    const int dy0 = max(0, static_cast<int>(static_cast<float>(y) / sy) - 1);
+    const int dy1 = min(prm.H, static_cast<int>(static_cast<float>(y + 1) / sy) + 2);
     for (int dx = threadIdx.x; dx < prm.W; dx += kMergeThreads) {
         const uint8_t c = row_cls[nearest_src(dx, sx, prm.w_lowres)];
         for (int dy = dy0; dy < dy1; ++dy)
