@@ -159,6 +159,14 @@ int vosprop_normalize_u8(const uint8_t* rgb, int64_t n_pixels /* n * H * W */, c
  * fills grid size and per-CTA [begin,end) of the linearised (m_tile, n_tile) space. */
 int vosprop_debug_decompose(int32_t n_pixels, int32_t n_refs, int32_t num_sms, int32_t* grid,
                             int64_t* cta_begin /* num_sms+1 entries or NULL */, int32_t* max_segments);
+/* Block skipping in the fused index-label kernel (off by default).  A 32 x 32 block of the affinity matrix whose logits all
+ * lie more than 127 (log2 units) below a lower bound of the final maximum of their rows weighs less than 2^-127 of the
+ * row's soft-max denominator per element -- at most ~1e-34 of a row's mass over all skipped blocks, 26 orders of magnitude
+ * below fp32 resolution -- and is left out.  With peaked embeddings (|f|^2 ~ 256) about two thirds of the blocks go and
+ * the mean busy time of a CTA drops by a quarter, but the kernel does not get shorter yet: the stream-K ranges balance
+ * tile counts, not work, and the CTAs that own the near-diagonal tiles set the pace.  It costs
+ * 2-3 % when nothing can be skipped.  Off everywhere until the tile assignment follows the work. */
+int vosprop_block_skip(vosprop_engine* e, int32_t enable);
 /* Development aid for profiling: a bit mask that switches off parts of the fused epilogue (bit 0: all per-step
  * arithmetic, 1: label gather, 2: prior, 3: running-max update, 4: prior and packed math).  Results are WRONG
  * with any bit set; production code never calls this (flags start at 0). */

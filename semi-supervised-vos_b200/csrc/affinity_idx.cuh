@@ -26,7 +26,8 @@ constexpr int kIdxThreads = 64 + kIdxEpiThreads;   // warp 0 TMA, warp 1 MMA, wa
 constexpr int kIdxSub = 4;           // partial records per (CTA, segment): one per 32-column quarter
 constexpr int kIdxRingChunks = 12;   // 12 x 16 KiB of reference chunks in flight, grouped into stages (IdxCfg)
 constexpr int kIdxMaxAccBufs = 3;
-constexpr int kIdxSmem = kIdxRingChunks * kChunkBytes + 512 + 1024;
+constexpr int kIdxRowMaxBytes = 4 * kTile * 4;   // block skipping: 4 segment-parity slots x 128 rows of shared running maxima
+constexpr int kIdxSmem = kIdxRingChunks * kChunkBytes + 512 + kIdxRowMaxBytes + 1024;
 
 // Precision-dependent shape of the pipeline.
 //   kSplit = true : fp32 features stored as bf16 hi + lo; S = Qhi.Rhi + Qlo.Rhi + Qhi.Rlo (3 MMA passes, 8 chunks of
@@ -463,13 +464,34 @@ __device__ __forceinline__ void chain_init(float a0, float b0, const PriorConst&
 // 16-column chains.  The first capture of the single-pass kernel showed every epilogue warp latency-bound on that
 // bookkeeping (~9 cycles per instruction, 4 warps per scheduler), not on MUFU or issue slots.
 // jw = first of the 32 columns that lies on the next image row (>= 32: none).
-template <int D, bool kWide>
+template <int D, bool kWide, bool kSkip>
 __device__ __forceinline__ void fast_tile32(RowAcc<D>& st, float (&va)[kQC], float (&vb)[kQC], uint32_t cls_lane, uint32_t cls0,
                                             uint32_t same32, int dn, float bx, int jw, const PriorConst& pc, float inv_w,
-                                            float scale2, float w_lowres) {
+                                            float scale2, float w_lowres, uint32_t& probe, volatile float* rm_row) {
     const uint32_t full = 0xffffffffu;
     {
-        const float m_new = fmaxf(st.m, fmaxf(max16(va), max16(vb)) * scale2);
+        const float bm = fmaxf(max16(va), max16(vb)) * scale2;
+        // Block skipping (kSkip instantiation, vosprop_block_skip).  If every logit of this warp's 32 x 32 block lies more
+        // than 127 (log2 units) below a lower bound of the final maximum of its row, each of its exponentials is below
+        // 2^-127 of the row's denominator: the whole affinity row can lose at most N x 2^-127 ~ 1e-34 of its mass that way,
+        // 26 orders of magnitude under fp32 resolution (and under the 1e-14 of the validation loss), so the block is left
+        // out.  The bound is the largest running maximum any of the four column-quarter warps of this row has published in
+        // shared memory (a racy, monotone-enough max: any value ever written is a true running maximum, hence a valid bound).
+        // Trained embeddings (|f|^2 ~ 256) make most of the affinity matrix such blocks; low-contrast synthetic clips make
+        // none.  The test costs a shared load and a warp vote: it runs on every 16th block and, after a dead block, on each
+        // of the next 64 blocks (`probe`: bits 16.. = blocks left in that window, low bits = block counter).
+        if constexpr (kSkip) {
+            probe = (probe & 0xffff0000u) | ((probe + 1u) & 0xffffu);
+            if ((probe >> 16) != 0u || (probe & 15u) == 0u) {
+                const float bound = fmaxf(st.m, *rm_row);
+                const bool dead = __all_sync(full, bm - bound < -127.f);
+                const uint32_t window = dead ? 64u : max(probe >> 16, 1u) - 1u;
+                probe = (probe & 0xffffu) | (window << 16);
+                if (dead) return;
+            }
+            if (bm > st.m && bm > *rm_row) *rm_row = bm;      // publish (bm becomes this warp's running maximum below)
+        }
+        const float m_new = fmaxf(st.m, bm);
         if (m_new > st.m) {
             const float corr = ex2(st.m - m_new);
             st.l *= corr;
@@ -583,7 +605,7 @@ __device__ __forceinline__ void fast_tile32(RowAcc<D>& st, float (&va)[kQC], flo
 // kWide: the frame-level bound that makes the prior recurrence safe everywhere (PriorConst::chain_always) fails for
 // some reference of this step (1080p with sigma = 8): tiles test themselves.  A separate instantiation, because the extra
 // live values cost the 96-register kernel 3.6 % at 480p.
-template <int D, bool kSplit, bool kWide>
+template <int D, bool kSplit, bool kWide, bool kSkip = false>
 __global__ void __launch_bounds__(kIdxThreads, 1)   // 18 warps: 5 on two of the schedulers -> 16384 / (5 * 32) = 96 registers
 vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
                  const __grid_constant__ AffinityParams prm) {
@@ -621,6 +643,15 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             idx_stage_target<kSplit>(pp, prm, it.seg, m_tile, row, lane_base, sub, kIdxSub);
             RowAcc<D> st;
             st.init();
+            uint32_t probe = 0;            // block-skipping state of fast_tile32 (warp-uniform)
+            volatile float* rm_row = nullptr;
+            if constexpr (kSkip) {
+                // this row's slot of the shared running maxima; 4 slots by segment parity because the warps of a CTA drift
+                // apart by fewer than 3 tiles (accumulator barriers), hence by fewer than 4 segments
+                uint8_t* aligned = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
+                rm_row = reinterpret_cast<volatile float*>(aligned + kIdxRingChunks * kChunkBytes + 512) + (it.seg & 3) * kTile + row;
+                *rm_row = kNegBig;
+            }
             const int m = m_tile * kTile + row;
             const int xm = m % W;
             // (reference frame r, tile j inside it) of the segment's first tile; afterwards incremental
@@ -653,7 +684,7 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_s(pp.acc_empty + 8 * buf);
-                    fast_tile32<D, kWide>(st, va, vb, cls_lane, cls0, same32, dn, static_cast<float>(x_sub - xm), W - x_sub, pc, inv_w, scale2, w_f);
+                    fast_tile32<D, kWide, kSkip>(st, va, vb, cls_lane, cls0, same32, dn, static_cast<float>(x_sub - xm), W - x_sub, pc, inv_w, scale2, w_f, probe, rm_row);
                 } else {
                 int xq = x_sub;
 #pragma unroll 1

@@ -70,6 +70,7 @@ struct vosprop_engine {
     uint8_t* low_scratch = nullptr;   // stride-8 class map when the caller wants only the full-resolution mask
     // decomposition tables of the merge kernel, one per reference count (cached until the next reset)
     int32_t* tables = nullptr;        // device [VOSPROP_MAX_REFS + 1][table_stride]
+    int block_skip = 0;               // vosprop_block_skip: fused kernel with exact skipping of all-zero blocks
     size_t table_stride = 0;
     std::vector<char> table_valid;
     CUtensorMap tmap_hi{}, tmap_lo{};
@@ -146,9 +147,10 @@ int launch_affinity(vosprop_engine* e, const vosk::AffinityParams& prm, int grid
             wide = wide || !(30.f * coef * (h * inv_w + w) - 225.f * gamma < 100.f);
         }
         const bool split = prm.feat_fmt == vosk::kFmtSplit;
+        const bool skip = e->block_skip && !wide;
         void (*kern)(CUtensorMap, CUtensorMap, vosk::AffinityParams) =
-            split ? (wide ? vosk::vos_affinity_idx<D, true, true> : vosk::vos_affinity_idx<D, true, false>)
-                  : (wide ? vosk::vos_affinity_idx<D, false, true> : vosk::vos_affinity_idx<D, false, false>);
+            split ? (wide ? vosk::vos_affinity_idx<D, true, true> : skip ? vosk::vos_affinity_idx<D, true, false, true> : vosk::vos_affinity_idx<D, true, false>)
+                  : (wide ? vosk::vos_affinity_idx<D, false, true> : skip ? vosk::vos_affinity_idx<D, false, false, true> : vosk::vos_affinity_idx<D, false, false>);
         VOS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kIdxSmem));
         VOS_CUDA(launch_pdl(kern, grid, vosk::kIdxThreads, vosk::kIdxSmem, st, e->tmap_hi, e->tmap_lo, prm));
     } else if (kernel == VOSPROP_KERNEL_TC_DENSE) {
@@ -637,6 +639,12 @@ int vosprop_plan_step(int32_t frame_idx, int32_t take_range, int32_t num_refs, f
         step->ref_sigma[r] = probability_propagation ? 0.f : sg;
     }
     step->probability_propagation = probability_propagation;
+    return VOSPROP_OK;
+}
+
+int vosprop_block_skip(vosprop_engine* e, int32_t enable) {
+    if (!e) return fail(VOSPROP_ERR_INVALID, "null engine");
+    e->block_skip = enable != 0;
     return VOSPROP_OK;
 }
 

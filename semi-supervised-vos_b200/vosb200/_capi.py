@@ -47,6 +47,7 @@ EXPORTS = {
     'vosprop_destroy': (None, [C.c_void_p]),
     'vosprop_reset': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     'vosprop_append_features': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    'vosprop_block_skip': (C.c_int, [C.c_void_p, C.c_int32]),
     'vosprop_normalize_u8': (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_int32,
                                        C.c_void_p]),
     'vosprop_append_frames': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,

@@ -112,6 +112,10 @@ class PropagationEngine:
     def launch_count(self) -> int:
         return self._lib.vosprop_launch_count(self._h)
 
+    def block_skip(self, enable: bool = True):
+        """Skipping of blocks whose soft-max weight is below fp32 underflow (vos_prop.h: vosprop_block_skip)."""
+        capi.check(self._lib.vosprop_block_skip(self._h, int(bool(enable))))
+
     def enable_timing(self, capacity: int, classes=('append', 'affinity', 'merge')):
         """Bracket the kernel launches of the given classes with CUDA events (bench.py roofline); 0 disables."""
         mask = sum(1 << ('append', 'affinity', 'merge').index(c) for c in classes)

@@ -36,6 +36,56 @@ def test_ten_objects_index_kernel(prec):
         assert err <= PROB_ATOL
 
 
+@pytest.mark.parametrize('prec,feat_scale', [('f16', 0.8), ('f16', 1.5), ('split3', 1.0)])
+def test_peaked_embeddings_exercise_block_skipping(prec, feat_scale):
+    """Embeddings with the norm of trained ones (|f|^2 ~ 250-1000: logit range of several hundred, soft-max dominated by a
+    few neighbours): most 32 x 32 blocks of the affinity matrix underflow to exactly zero and the fused kernel leaves them
+    out when asked to (vosprop_block_skip; fast_tile32) -- equal to the kernel that computes them up to fp32 underflow.  Teacher-forced
+    steps and a whole clip with label feedback against the oracle."""
+    from vosb200 import PREC_F16, PREC_SPLIT3, plan_refs
+    from vosb200.sequence import propagate_clip
+    T = 14
+    feats, first = O.synthetic_sequence(T, 272, 400, 3, seed=91, feat_scale=feat_scale)
+    if prec == 'f16':
+        feats = feats.half().float()
+    _, K, H_d, W_d = feats.shape
+    P = H_d * W_d
+    logits = (feats[0].reshape(K, -1).t() @ feats[1].reshape(K, -1)) * 1.4427
+    dead = float((logits < logits.max(0, keepdim=True).values - 127).float().mean())
+    low, d = O.first_frame_labels(first)
+    g = torch.Generator().manual_seed(4)
+    cls = torch.randint(0, d, (T, (H_d + 7) // 8, (W_d + 7) // 8), generator=g).repeat_interleave(8, 1).repeat_interleave(8, 2)
+    cls = cls[:, :H_d, :W_d].reshape(T, P)
+    cls[0] = low
+    hist = torch.stack([O.index_to_onehot(cls[f], d) for f in range(T)], 1)
+    eng, plain = _engine(P), _engine(P)
+    eng.block_skip(True)
+    gf = feats.cuda().half() if prec == 'f16' else feats.cuda()
+    for e in (eng, plain):
+        e.reset(H_d, W_d, 272, 400, d, PREC_F16 if prec == 'f16' else PREC_SPLIT3)
+        for f in range(T):
+            e.append(f, gf[f])
+            e.set_labels_index(f, cls[f].to(torch.uint8).cuda())
+    for t in (1, 6, 13):
+        refs, sig = plan_refs(t, 40, 9, 8.0, 21.0, False)
+        got = eng.propagate(t, refs, sig, 1.0, False, write_labels=False)['prediction']
+        ref = plain.propagate(t, refs, sig, 1.0, False, write_labels=False)['prediction']
+        assert float((got - ref).abs().max()) < 1e-30       # skipped mass is below fp32 underflow relative to the row sum
+        got = got.cpu()
+        want = O.predict(feats[:t], feats[t], hist[:, :t], 8.0, 21.0, t, 40, 9, 1.0, False)
+        err = float((got - want).abs().max())
+        agree = float((got.argmax(0) == want.argmax(0)).float().mean())
+        print(f'peaked {prec} scale {feat_scale} ({dead:.0%} of logits > 127 below their row max) t={t}: max |dP| {err:.2e}, '
+              f'arg-max agreement {agree:.5f}')
+        assert err <= PROB_ATOL and agree >= MASK_AGREE
+        assert torch.isfinite(got).all()
+    masks, preds = propagate_clip(eng, gf, first, return_predictions=True)
+    want_masks, want_preds = O.propagate_sequence(feats, first)
+    agree = float((masks.cpu().long() == want_masks).float().mean())
+    print(f'peaked {prec} scale {feat_scale} clip: mask agreement {agree:.6f}')
+    assert agree >= MASK_AGREE and dead > 0.5
+
+
 @pytest.mark.parametrize('ref_num,frame_range', [(3, 40), (4, 40), (5, 10), (12, 40), (20, 40), (9, 2)])
 def test_ref_num_and_range_sweep(ref_num, frame_range):
     """Whole clips long enough to leave the ramp (frame_idx > ref_num), pass frame 15 (sigma switch) and wrap the

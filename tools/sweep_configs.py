@@ -21,20 +21,36 @@ from vosb200.sequence import lowres_dims  # noqa: E402
 K = 256
 
 
-def measure(H, W, n_obj, ref_num, topk, prec, frames=8, t0=46, probability=False, warm=3):
+def measure(H, W, n_obj, ref_num, topk, prec, frames=8, t0=46, probability=False, warm=3, proto_scale=0.3, noise=0.1,
+            block_skip=False, field_len=0.0):
     dev = torch.device('cuda', 0)
     T = t0 + warm + frames
     H_d, W_d = lowres_dims(H, W)
     P = H_d * W_d
     g = torch.Generator(device=dev).manual_seed(1)
-    proto = torch.randn(n_obj + 1, K, device=dev, generator=g) * 0.3
+    proto = torch.randn(n_obj + 1, K, device=dev, generator=g) * proto_scale
     eng = PropagationEngine(max_pixels=P, ring_slots=max(48, ref_num + 2), device=dev)
     eng.reset(H_d, W_d, H, W, n_obj + 1, prec)
+    eng.block_skip(block_skip)
     cm = synthetic._class_map(synthetic._tracks(n_obj, torch.Generator().manual_seed(2)), 0, H_d, W_d, dev).reshape(-1)
     feat_dtype = torch.float16 if prec == PREC_F16 else torch.float32
 
+    field = None
+    if field_len > 0:
+        # appearance that varies over the image like a texture: random Fourier features of the pixel position with
+        # correlation length `field_len` (stride-8 pixels) and |f|^2 = 256 -- two pixels further apart than ~1.5 lengths
+        # have nearly orthogonal embeddings, as different surfaces have in a trained network
+        ys, xs = torch.meshgrid(torch.arange(H_d, device=dev, dtype=torch.float32), torch.arange(W_d, device=dev, dtype=torch.float32), indexing='ij')
+        pos = torch.stack([ys.reshape(-1), xs.reshape(-1)], 1)
+        w = torch.randn(2, K, device=dev, generator=g) / field_len
+        b = torch.rand(K, device=dev, generator=g) * 6.2831853
+        field = torch.cos(pos @ w + b) * (2.0 / K) ** 0.5 * 16.0
+
     def feature(t):
-        f = proto[cm] + 0.1 * torch.randn(P, K, device=dev, generator=g)
+        if field is not None:
+            f = field + proto[cm] + noise * torch.randn(P, K, device=dev, generator=g)
+        else:
+            f = proto[cm] + noise * torch.randn(P, K, device=dev, generator=g)
         return f.t().reshape(K, H_d, W_d).to(feat_dtype).contiguous()
 
     onehot = torch.zeros(n_obj + 1, P, device=dev).scatter_(0, cm.view(1, -1), 1.0)
@@ -66,6 +82,15 @@ def measure(H, W, n_obj, ref_num, topk, prec, frames=8, t0=46, probability=False
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == 'peaked':
+        # embedding norm of trained features (|f|^2 ~ 256) instead of the low-contrast bench clips (|f|^2 ~ 26): blocks of the
+        # affinity matrix that underflow to exactly zero are skipped by the fused kernel
+        for ps, nz, fl in ((0.3, 0.1, 0.0), (0.95, 0.3, 0.0), (0.3, 0.1, 12.0), (0.3, 0.1, 6.0), (0.3, 0.1, 3.0)):
+            for skip in (False, True):
+                r = measure(480, 854, 2, 9, 0, PREC_F16, proto_scale=ps, noise=nz, block_skip=skip, field_len=fl)
+                print(json.dumps(dict(config='peaked', class_prototype_norm2=round(K * ps * ps, 1), noise_norm2=round(K * nz * nz, 1),
+                                      texture_field='none' if not fl else f'|f|^2 = 256, correlation length {fl} px', block_skip=skip, **r)), flush=True)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'prob':
         for prec in (PREC_F16, PREC_SPLIT3):
             print(json.dumps(dict(config='prob', **measure(480, 854, 2, 9, 0, prec, probability=True))), flush=True)
