@@ -467,7 +467,7 @@ __device__ __forceinline__ void chain_init(float a0, float b0, const PriorConst&
 template <int D, bool kWide, bool kSkip>
 __device__ __forceinline__ void fast_tile32(RowAcc<D>& st, float (&va)[kQC], float (&vb)[kQC], uint32_t cls_lane, uint32_t cls0,
                                             uint32_t same32, int dn, float bx, int jw, const PriorConst& pc, float inv_w,
-                                            float scale2, float w_lowres, uint32_t& probe, volatile float* rm_row) {
+                                            float scale2, float w_lowres, uint32_t& probe, volatile float* rm_row, bool row_real) {
     const uint32_t full = 0xffffffffu;
     {
         const float bm = fmaxf(max16(va), max16(vb)) * scale2;
@@ -484,7 +484,8 @@ __device__ __forceinline__ void fast_tile32(RowAcc<D>& st, float (&va)[kQC], flo
             probe = (probe & 0xffff0000u) | ((probe + 1u) & 0xffffu);
             if ((probe >> 16) != 0u || (probe & 15u) == 0u) {
                 const float bound = fmaxf(st.m, *rm_row);
-                const bool dead = __all_sync(full, bm - bound < -127.f);
+                // rows beyond the frame's last pixel (ragged last target tile) are discarded by the merge: they never veto
+                const bool dead = __all_sync(full, !row_real || bm - bound < -127.f);
                 const uint32_t window = dead ? 64u : max(probe >> 16, 1u) - 1u;
                 probe = (probe & 0xffffu) | (window << 16);
                 if (dead) return;
@@ -684,7 +685,7 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_s(pp.acc_empty + 8 * buf);
-                    fast_tile32<D, kWide, kSkip>(st, va, vb, cls_lane, cls0, same32, dn, static_cast<float>(x_sub - xm), W - x_sub, pc, inv_w, scale2, w_f, probe, rm_row);
+                    fast_tile32<D, kWide, kSkip>(st, va, vb, cls_lane, cls0, same32, dn, static_cast<float>(x_sub - xm), W - x_sub, pc, inv_w, scale2, w_f, probe, rm_row, m < prm.n_pixels);
                 } else {
                 int xq = x_sub;
 #pragma unroll 1
