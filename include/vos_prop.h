@@ -163,8 +163,8 @@ int vosprop_debug_decompose(int32_t n_pixels, int32_t n_refs, int32_t num_sms, i
  * lie more than 127 (log2 units) below a lower bound of the final maximum of their rows weighs less than 2^-127 of the
  * row's soft-max denominator per element -- at most ~1e-34 of a row's mass over all skipped blocks, 26 orders of magnitude
  * below fp32 resolution -- and is left out.  With peaked embeddings (|f|^2 ~ 256) about two thirds of the blocks go and
- * the mean busy time of a CTA drops by a quarter; the launch gets 6-9 % shorter (the stream-K ranges balance tile counts,
- * not work, so the busiest CTA sets the pace).  It costs 3-4 % when nothing can be skipped. */
+ * the launch gets 10-17 % shorter (reference tiles are then visited in a strided order that spreads the live tiles over
+ * the CTAs).  It costs about 6 % when nothing can be skipped. */
 int vosprop_block_skip(vosprop_engine* e, int32_t enable);
 /* Development aid for profiling: a bit mask that switches off parts of the fused epilogue (bit 0: all per-step
  * arithmetic, 1: label gather, 2: prior, 3: running-max update, 4: prior and packed math).  Results are WRONG

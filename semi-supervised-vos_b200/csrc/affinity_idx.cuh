@@ -79,7 +79,9 @@ __device__ __forceinline__ void idx_role_producer(const IdxPipe& pp, const CUten
     while (it.next(m_tile, n0, n1)) {
         for (int nt = n0; nt < n1; ++nt) {
             const int r = nt / dec.tpf;
-            int row0 = prm.ref_slot[r] * prm.p_pad + (nt - r * dec.tpf) * kTile;
+            int jt = nt - r * dec.tpf;
+            if (prm.tile_stride > 1) jt = (jt * prm.tile_stride) % dec.tpf;      // work-balancing tile order (block skipping)
+            int row0 = prm.ref_slot[r] * prm.p_pad + jt * kTile;
             if (prm.dbg & 64) row0 = 0;                  // profiling: every CTA streams the same tile
 #pragma unroll
             for (int g = 0; g < kChunks / kGroup; ++g) {
@@ -658,9 +660,20 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             // (reference frame r, tile j inside it) of the segment's first tile; afterwards incremental
             int r = n0 / dec.tpf;
             int j = n0 - r * dec.tpf;
-            int x_sub = (j * kTile + sub * 32) % W;       // image column of this warp's first logit column
-            int dn = j * kTile + sub * 32 - m;            // pixel-index difference of that column to the target pixel
-            const uint8_t* cls_p = prm.cls + static_cast<size_t>(prm.ref_slot[r]) * prm.p_pad + j * kTile + sub * 32 + lane;
+            // kSkip: the tiles of a reference frame are visited in a strided order (tile jp = j * stride mod tiles-per-frame,
+            // stride coprime: a permutation), so that the live tiles around the diagonal are spread evenly over the linear
+            // tile space and every CTA's range holds its share of them.  jp and everything derived from it advance
+            // incrementally (one add and one conditional subtract per tile; the modulos are taken once per segment).
+            int jp = j;
+            int xs_step = 0, xs_wrap = 0;
+            if constexpr (kSkip) {
+                jp = (j * prm.tile_stride) % dec.tpf;
+                xs_step = (prm.tile_stride * kTile) % W;
+                xs_wrap = (dec.tpf * kTile) % W;
+            }
+            int x_sub = (jp * kTile + sub * 32) % W;      // image column of this warp's first logit column
+            int dn = jp * kTile + sub * 32 - m;           // pixel-index difference of that column to the target pixel
+            const uint8_t* cls_p = prm.cls + static_cast<size_t>(prm.ref_slot[r]) * prm.p_pad + jp * kTile + sub * 32 + lane;
             PriorConst pc = prior_const(prm.ref_coef[r], inv_w, w_f, h_f);
             uint32_t cls_next = __ldg(cls_p);                        // class byte of logit column `lane`, one tile ahead
             for (int nt = n0; nt < n1; ++nt) {
@@ -669,9 +682,15 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                     const bool wrap_ref = j + 1 == dec.tpf;
                     const uint8_t* nxt = wrap_ref ? prm.cls + static_cast<size_t>(prm.ref_slot[min(r + 1, prm.n_refs - 1)]) * prm.p_pad + sub * 32 + lane
                                                   : cls_p + kTile;
+                    if constexpr (kSkip) {
+                        if (!wrap_ref) {
+                            const int jn = jp + prm.tile_stride;
+                            nxt = cls_p + ((jn >= dec.tpf ? jn - dec.tpf : jn) - jp) * kTile;
+                        }
+                    }
                     if (nt + 1 < n1) cls_next = __ldg(nxt);
                 }
-                const uint32_t valid32 = (j == dec.tpf - 1) ? ragged : full;
+                const uint32_t valid32 = (jp == dec.tpf - 1) ? ragged : full;
                 mbar_wait_s(pp.acc_full + 8 * buf, aphase);
                 tc_fence_after_sync();
                 const uint32_t taddr = pp.tmem_base + lane_base + buf * kTile + sub * 32;
@@ -759,6 +778,7 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                 // next tile: 128 pixels further in the same frame, or tile 0 of the next reference frame
                 if (++j == dec.tpf) {
                     j = 0;
+                    jp = 0;
                     ++r;
                     x_sub = (sub * 32) % W;
                     dn = sub * 32 - m;
@@ -766,7 +786,19 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                         pc = prior_const(prm.ref_coef[r], inv_w, w_f, h_f);
                         cls_p = prm.cls + static_cast<size_t>(prm.ref_slot[r]) * prm.p_pad + sub * 32 + lane;
                     }
+                } else if constexpr (kSkip) {
+                    int step = prm.tile_stride;               // tiles forward; minus a whole frame when the index wraps
+                    x_sub += xs_step;
+                    if (jp + step >= dec.tpf) {
+                        step -= dec.tpf;
+                        x_sub -= xs_wrap;
+                    }
+                    jp += step;
+                    x_sub = x_sub >= W ? x_sub - W : (x_sub < 0 ? x_sub + W : x_sub);
+                    dn += step * kTile;
+                    cls_p += step * kTile;
                 } else {
+                    jp = j;
                     x_sub += x_step;
                     if (x_sub >= W) x_sub -= W;
                     dn += kTile;

@@ -69,6 +69,7 @@ struct AffinityParams {
     uint32_t* cand_key;   // [grid * max_segs][128][kTopkMax] order-preserving keys of logit * temperature
     int32_t* cand_idx;    // same shape: reference index r*P + pixel
     int32_t* cand_cnt;    // [grid * max_segs][128]
+    int32_t tile_stride;  // 0/1, or (block skipping) the stride of the permuted tile order inside a reference frame
     int32_t dbg;          // development aid (vosprop_debug_flags): disables parts of the epilogue; 0 in production
     long long* dbg_clk;   // development aid: per-CTA cycle counters of the role warps' waits (null in production)
 };

@@ -148,11 +148,20 @@ int launch_affinity(vosprop_engine* e, const vosk::AffinityParams& prm, int grid
         }
         const bool split = prm.feat_fmt == vosk::kFmtSplit;
         const bool skip = e->block_skip && !wide;
+        vosk::AffinityParams prm_k = prm;
+        prm_k.tile_stride = 1;
+        if (skip) {   // golden-section stride, coprime with the tiles per frame: live (near-diagonal) tiles spread evenly
+            const int tpf = (prm.n_pixels + vosk::kTile - 1) / vosk::kTile;
+            int s = std::max(1, static_cast<int>(tpf * 0.381966f + 0.5f));
+            auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+            while (s < tpf && gcd(s, tpf) != 1) ++s;
+            prm_k.tile_stride = s < tpf ? s : 1;
+        }
         void (*kern)(CUtensorMap, CUtensorMap, vosk::AffinityParams) =
             split ? (wide ? vosk::vos_affinity_idx<D, true, true> : skip ? vosk::vos_affinity_idx<D, true, false, true> : vosk::vos_affinity_idx<D, true, false>)
                   : (wide ? vosk::vos_affinity_idx<D, false, true> : skip ? vosk::vos_affinity_idx<D, false, false, true> : vosk::vos_affinity_idx<D, false, false>);
         VOS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kIdxSmem));
-        VOS_CUDA(launch_pdl(kern, grid, vosk::kIdxThreads, vosk::kIdxSmem, st, e->tmap_hi, e->tmap_lo, prm));
+        VOS_CUDA(launch_pdl(kern, grid, vosk::kIdxThreads, vosk::kIdxSmem, st, e->tmap_hi, e->tmap_lo, prm_k));
     } else if (kernel == VOSPROP_KERNEL_TC_DENSE) {
         VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kSmemTc));
         vosk::vos_affinity_tc<D><<<grid, vosk::kTcThreads, vosk::kSmemTc, st>>>(e->tmap_hi, e->tmap_lo, prm);

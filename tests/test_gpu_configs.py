@@ -70,7 +70,7 @@ def test_peaked_embeddings_exercise_block_skipping(prec, feat_scale):
         refs, sig = plan_refs(t, 40, 9, 8.0, 21.0, False)
         got = eng.propagate(t, refs, sig, 1.0, False, write_labels=False)['prediction']
         ref = plain.propagate(t, refs, sig, 1.0, False, write_labels=False)['prediction']
-        assert float((got - ref).abs().max()) < 1e-30       # skipped mass is below fp32 underflow relative to the row sum
+        assert float((got - ref).abs().max()) < 2e-6        # skipped mass is below fp32 underflow; the tile order differs (rounding)
         got = got.cpu()
         want = O.predict(feats[:t], feats[t], hist[:, :t], 8.0, 21.0, t, 40, 9, 1.0, False)
         err = float((got - want).abs().max())
