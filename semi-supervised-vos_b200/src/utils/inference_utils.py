@@ -9,6 +9,8 @@ per video.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 from tqdm import tqdm
@@ -25,6 +27,10 @@ REDUCTIONS = {'maximum': lambda x, y: torch.maximum(x, y),
               'mean': lambda x, y: (x + y) / 2.0}
 
 _ENGINES = {}
+# VOS_BLOCK_SKIP=1: the fused kernel leaves out blocks of the affinity matrix whose soft-max weight is below fp32 underflow
+# (vos_prop.h: vosprop_block_skip).  10-17 % faster propagation on embeddings as peaked as trained ones, 6 % slower on
+# low-contrast ones; off unless asked for.
+_BLOCK_SKIP = os.environ.get('VOS_BLOCK_SKIP', '0') == '1'
 
 
 def _require_cuda() -> torch.device:
@@ -43,6 +49,7 @@ def _engine_for(n_pixels: int, slots: int) -> PropagationEngine:
         if eng is not None:
             eng.close()
         eng = _ENGINES[key] = PropagationEngine(max_pixels=n_pixels, ring_slots=max(slots, 48), device=dev)
+        eng.block_skip(_BLOCK_SKIP)
     return eng
 
 
@@ -242,6 +249,7 @@ class _Stream:
             if self.engine is not None:
                 self.engine.close()
             self.engine = PropagationEngine(max_pixels=n_pixels, ring_slots=max(self.slots, 48), device=features.device)
+            self.engine.block_skip(_BLOCK_SKIP)
         self.geom = (H_d, W_d, H, W, int(d))
         self.engine.reset(H_d, W_d, H, W, int(d), precision_for(features.dtype))
         self.engine.append(0, features)
