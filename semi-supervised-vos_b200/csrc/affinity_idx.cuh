@@ -18,12 +18,30 @@
 #pragma once
 #include "kernels.cuh"
 
+// Profiling aids (vosprop_debug_flags / vosprop_debug_clocks) are compiled in only with -DVOS_KERNEL_DEBUG (tools/epilogue_ablation.py
+// builds such a library); the product kernels carry no clock reads and no flag tests.
+#ifdef VOS_KERNEL_DEBUG
+#define VOS_DBG(prm, bits) (((prm).dbg & (bits)) != 0)
+#define VOS_DBG_ANY(prm) ((prm).dbg != 0)
+#define VOS_CLK() clock64()
+#else
+#define VOS_DBG(prm, bits) false
+#define VOS_DBG_ANY(prm) false
+#define VOS_CLK() 0ll
+#endif
+
+// Timing experiments on the fast tile path (tools/gpu_ab.sh builds variants with -DVOS_ABL=<bits>; results are WRONG with
+// any bit set): 1 no MUFU for the logits, 2 no Horner chain, 4 no running-max update, 8 every block takes the simple path,
+// 16 no denominator sum, 32 no chain set-up / finish, 64 no TMEM loads, 128 no class bytes.
+#ifndef VOS_ABL
+#define VOS_ABL 0
+#endif
+
 namespace vosk {
 
 constexpr int kIdxEpiWarps = 16;     // 4 per scheduler: each owns 32 TMEM lanes x 32 logit columns of a tile
 constexpr int kIdxEpiThreads = kIdxEpiWarps * 32;
 constexpr int kIdxThreads = 64 + kIdxEpiThreads;   // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue
-constexpr int kIdxSub = 4;           // partial records per (CTA, segment): one per 32-column quarter
 constexpr int kIdxRingChunks = 12;   // 12 x 16 KiB of reference chunks in flight, grouped into stages (IdxCfg)
 constexpr int kIdxMaxAccBufs = 3;
 constexpr int kIdxRowMaxBytes = 4 * kTile * 4;   // block skipping: 4 segment-parity slots x 128 rows of shared running maxima
@@ -75,22 +93,22 @@ __device__ __forceinline__ void idx_role_producer(const IdxPipe& pp, const CUten
     vosd::SegIter it(dec, blockIdx.x);
     int m_tile, n0, n1;
     uint32_t stage = 0, phase = 0;
-    long long t_wait = 0, t_begin = clock64();
+    long long t_wait = 0, t_begin = VOS_CLK();
     while (it.next(m_tile, n0, n1)) {
         for (int nt = n0; nt < n1; ++nt) {
             const int r = nt / dec.tpf;
             int jt = nt - r * dec.tpf;
             if (prm.tile_stride > 1) jt = (jt * prm.tile_stride) % dec.tpf;      // work-balancing tile order (block skipping)
             int row0 = prm.ref_slot[r] * prm.p_pad + jt * kTile;
-            if (prm.dbg & 64) row0 = 0;                  // profiling: every CTA streams the same tile
+            if (VOS_DBG(prm, 64)) row0 = 0;              // profiling: every CTA streams the same tile
 #pragma unroll
             for (int g = 0; g < kChunks / kGroup; ++g) {
-                const long long t0 = clock64();
+                const long long t0 = VOS_CLK();
                 mbar_wait_relaxed_s(pp.empty + 8 * stage, phase ^ 1, 64);
-                t_wait += clock64() - t0;
+                t_wait += VOS_CLK() - t0;
                 if (elect_one()) {
                     const uint32_t bar = pp.full + 8 * stage;
-                    if (prm.dbg & 128) {                 // profiling: no loads at all (MMA on stale shared memory)
+                    if (VOS_DBG(prm, 128)) {             // profiling: no loads at all (MMA on stale shared memory)
                         mbar_arrive_s(bar);
                     } else {
                         mbar_arrive_expect_tx_s(bar, kStageBytes);
@@ -108,10 +126,14 @@ __device__ __forceinline__ void idx_role_producer(const IdxPipe& pp, const CUten
             }
         }
     }
+#ifdef VOS_KERNEL_DEBUG
     if (prm.dbg_clk && (threadIdx.x & 31) == 0) {
         prm.dbg_clk[blockIdx.x * 16 + 0] = clock64() - t_begin;
         prm.dbg_clk[blockIdx.x * 16 + 1] = t_wait;
     }
+#else
+    (void)t_wait; (void)t_begin;
+#endif
 }
 
 // MMA issuer (one warp, one elected lane issues): D[tmem] += Q[tmem] . R[smem]^T
@@ -125,25 +147,27 @@ __device__ __forceinline__ void idx_role_mma(const IdxPipe& pp, const AffinityPa
     uint32_t stage = 0, phase = 0, buf = 0, aphase = 0;
     const uint32_t q_hi = pp.tmem_base + Cfg::kTmemQ, q_lo = pp.tmem_base + Cfg::kTmemQ + 128;
     const uint64_t desc0 = umma_desc_kmajor_sw128(pp.r_smem);
-    long long t_q = 0, t_acc = 0, t_full = 0, t_begin = clock64();
+    long long t_q = 0, t_acc = 0, t_full = 0, t_begin = VOS_CLK();
+#ifdef VOS_KERNEL_DEBUG
     unsigned long long ns_begin;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_begin));
+#endif
     while (it.next(m_tile, n0, n1)) {
-        long long t0 = clock64();
+        long long t0 = VOS_CLK();
         mbar_wait_s(pp.q_full, it.seg & 1);
-        t_q += clock64() - t0;
+        t_q += VOS_CLK() - t0;
         tc_fence_after_sync();
         for (int nt = n0; nt < n1; ++nt) {
-            t0 = clock64();
+            t0 = VOS_CLK();
             mbar_wait_relaxed_s(pp.acc_empty + 8 * buf, aphase ^ 1, 32);
-            t_acc += clock64() - t0;
+            t_acc += VOS_CLK() - t0;
             tc_fence_after_sync();
             const uint32_t d_tmem = pp.tmem_base + buf * kTile;
 #pragma unroll
             for (int g = 0; g < Cfg::kChunks / kGroup; ++g) {
-                t0 = clock64();
+                t0 = VOS_CLK();
                 mbar_wait_s(pp.full + 8 * stage, phase);
-                t_full += clock64() - t0;
+                t_full += VOS_CLK() - t0;
                 tc_fence_after_sync();
                 if (elect_one()) {
                     // stage s starts s*kStageBytes after stage 0 ((addr >> 4) field); chunk i: +1024; K-step k: +2
@@ -166,8 +190,8 @@ __device__ __forceinline__ void idx_role_mma(const IdxPipe& pp, const AffinityPa
                                 for (int k = 0; k < kKC / 16; ++k)
                                     umma_bf16_ts(d_tmem, q_hi + (kc * 4 + k) * 8, b_desc + 2 * k, idesc, 1);
                             }
-                        } else if (prm.dbg & 256) {       // profiling: no tensor work at all
-                        } else if (prm.dbg & 512) {       // profiling: consecutive UMMAs into different accumulators
+                        } else if (VOS_DBG(prm, 256)) {   // profiling: no tensor work at all
+                        } else if (VOS_DBG(prm, 512)) {   // profiling: consecutive UMMAs into different accumulators
 #pragma unroll
                             for (int k = 0; k < kKC / 16; ++k)
                                 umma_bf16_ts(pp.tmem_base + ((k & 1) ? 128u : 0u), q_hi + (c * 4 + k) * 8, b_desc + 2 * k, idesc, (c | k) != 0);
@@ -188,6 +212,7 @@ __device__ __forceinline__ void idx_role_mma(const IdxPipe& pp, const AffinityPa
         if (elect_one()) umma_commit_s(pp.q_empty);
         __syncwarp();
     }
+#ifdef VOS_KERNEL_DEBUG
     if (prm.dbg_clk && (threadIdx.x & 31) == 0) {
         prm.dbg_clk[blockIdx.x * 16 + 2] = clock64() - t_begin;
         prm.dbg_clk[blockIdx.x * 16 + 3] = t_q;
@@ -199,6 +224,9 @@ __device__ __forceinline__ void idx_role_mma(const IdxPipe& pp, const AffinityPa
         prm.dbg_clk[blockIdx.x * 16 + 7] = static_cast<long long>(ns_begin);
         prm.dbg_clk[blockIdx.x * 16 + 8] = static_cast<long long>(ns_end);
     }
+#else
+    (void)t_q; (void)t_acc; (void)t_full; (void)t_begin;
+#endif
 }
 
 // Epilogue threads stage one segment's target tile into TMEM.  `n_sub` column groups (warps with the same
@@ -323,6 +351,9 @@ struct PriorConst {
     float gamma;   // -coef * (1 + 1/W^2)
     float k8;      // 2^(8*gamma)
     float k2;      // 2^(2*gamma)
+    float k8inv;   // 2^(-8*gamma)   Horner form (fast_tile32, !kWide): ratio step of the per-pair multipliers
+    float k52;     // 2^(52*gamma)
+    float k1;      // 2^gamma
     bool chain_always;   // the recurrence of step16_chain is safe for every (target, reference) pair of this frame
 };
 __device__ __forceinline__ PriorConst prior_const(float coef, float inv_w, float w_lowres, float h_lowres) {
@@ -331,8 +362,13 @@ __device__ __forceinline__ PriorConst prior_const(float coef, float inv_w, float
     pc.gamma = -coef * fmaf(inv_w, inv_w, 1.0f);
     pc.k8 = ex2(8.f * pc.gamma);
     pc.k2 = ex2(2.f * pc.gamma);
-    // |beta| <= 2*coef*(|drc|/W + |bx|) <= 2*coef*(H_d/W + W): exponent spread inside a 16-column step
-    pc.chain_always = fmaf(30.f * coef, fmaf(h_lowres, inv_w, w_lowres), -225.f * pc.gamma) < 100.f;
+    pc.k8inv = ex2(-8.f * pc.gamma);
+    pc.k52 = ex2(52.f * pc.gamma);
+    pc.k1 = ex2(pc.gamma);
+    // |beta| <= 2*coef*(|drc|/W + |bx|) <= 2*coef*(H_d/W + W + 16): exponent spread inside a 16-column step
+    // (+16: the masked Horner passes of a step with an image-row wrap evaluate the parabola of either row over all 16 columns,
+    //  i.e. up to 16 virtual columns beyond the row's end)
+    pc.chain_always = fmaf(30.f * coef, fmaf(h_lowres, inv_w, w_lowres + 16.f), -225.f * pc.gamma) < 100.f;
     return pc;
 }
 
@@ -460,6 +496,72 @@ __device__ __forceinline__ void chain_init(float a0, float b0, const PriorConst&
     scale = ex2(sh);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Horner form of the prior-weighted sum of one 16-column step (the 480p product path, !kWide).
+//   sum_j p_j g(j),  g(j) = 2^(a + b j + gamma j^2)  (j = 0..15: consecutive reference pixels on one image row)
+// With r(j) = g(j+2)/g(j) = 2^(2b + 4 gamma + 4 gamma j) the even and the odd columns are two nested products
+//   S_k = P_k + R_k * S_{k+1},  P_k = (p_2k, p_2k+1),  R_k = (r(2k), r(2k+1)),  R_{k-1} = R_k * 2^(-8 gamma),  k = 6..0,  S_7 = P_7
+//   sum = g(0) * (S_0.x + 2^(b + gamma) * S_0.y)
+// i.e. ONE FFMA2 + ONE FMUL2 per column pair, against four packed operations for the forward recurrence of step16_chain
+// (weight, running sum, G, Rho).  The FMA pipe carries as many cycles per tile as the tensor pipe in this kernel, so the
+// instruction count is what matters.  Set-up: two MUFU per step (2^b, 2^(a/2)).  The partial sums are relative to g(2k):
+// inside PriorConst::chain_always' bound (exponent spread of a step < 100) they stay far from fp32 overflow, and g(0) is
+// applied as h*h with h = 2^(a/2), so a very negative `a` underflows only where g(0)*S itself is below fp32 (where
+// exp(-d^2/sigma^2) of the reference, predict.py:173, is a denormal or 0 as well).  Relative error of the multipliers:
+// 7 x that of one MUFU.EX2 (~1.5e-6), the same as the forward recurrence.
+struct HornerStep {
+    float2 R;     // (r(12), r(13)) on entry to the chain
+    float qk;     // g(1)/g(0) = 2^(b + gamma)
+    float h;      // 2^(a/2)
+};
+__device__ __forceinline__ HornerStep horner_init(float a, float b, const PriorConst& pc) {
+    HornerStep hs;
+    const float q = ex2(b);
+    hs.h = ex2(0.5f * a);
+    const float r12 = q * q * pc.k52;                  // 2^(2b + 52 gamma)
+    hs.R = make_float2(r12, r12 * (pc.k2 * pc.k2));    // r(13) = r(12) * 2^(4 gamma)
+    hs.qk = q * pc.k1;
+    return hs;
+}
+__device__ __forceinline__ float horner_finish(const HornerStep& hs, float2 S) {
+    return fmaf(hs.qk, S.y, S.x) * hs.h * hs.h;
+}
+
+// One 16-column step whose columns do not all share (class, image row): for each image-row segment ([0, jwh) on the
+// row of column 0, [jwh, 16) on the next one: x jumps back by W) and each class present in it, a Horner pass over the
+// exponentials p[] masked to those columns.  cls_lane / lane_shift as in gather_mixed; everything but p[] and the
+// coefficients is warp-uniform.  One masked sum per class present -- no class takes "the step total minus the others"
+// (see gather_mixed).
+template <int D>
+__device__ __forceinline__ void horner_general16(RowAcc<D>& st, const float (&p)[kQC], uint32_t cls_lane, int lane_shift, int jwh,
+                                                 float drc, float bx, const PriorConst& pc, float inv_w, float w_lowres) {
+    const uint32_t full = 0xffffffffu;
+    const float2 K8i = make_float2(pc.k8inv, pc.k8inv);
+    const uint32_t row0 = jwh >= kQC ? 0xffffu : ((1u << jwh) - 1u);      // columns on the image row of column 0
+#pragma unroll 1
+    for (int seg = 0; seg < 2; ++seg) {
+        uint32_t rem = seg == 0 ? row0 : (0xffffu & ~row0);
+        if (rem == 0u) continue;
+        float a, b;
+        quad_coeffs(drc, seg == 0 ? bx : bx - w_lowres, inv_w, pc.coef, 0.f, a, b);
+        const HornerStep hs = horner_init(a, b, pc);
+        while (rem != 0u) {
+            const uint32_t c = __shfl_sync(full, cls_lane, lane_shift + __ffs(rem) - 1);
+            const uint32_t mk = (__ballot_sync(full, cls_lane == c) >> lane_shift) & rem;
+            float2 R = hs.R;
+            float2 S = make_float2(((mk >> 14) & 1u) ? p[14] : 0.f, ((mk >> 15) & 1u) ? p[15] : 0.f);
+#pragma unroll
+            for (int k = 6; k >= 0; --k) {
+                const float2 P = make_float2(((mk >> (2 * k)) & 1u) ? p[2 * k] : 0.f, ((mk >> (2 * k + 1)) & 1u) ? p[2 * k + 1] : 0.f);
+                S = ffma2(R, S, P);
+                if (k > 0) R = fmul2(R, K8i);
+            }
+            add_to_class<D>(st, static_cast<int>(c), horner_finish(hs, S));
+            rem &= ~mk;
+        }
+    }
+}
+
 // ---- Fast tile path: this warp's 32 columns are all real and the recurrence is safe for the whole frame
 // (PriorConst::chain_always).  Per-step bookkeeping (validity masks, path selection) is decided once per tile by the
 // caller; the common case (no image-row wrap inside the 32 columns) is straight-line code with two independent
@@ -495,7 +597,7 @@ __device__ __forceinline__ void fast_tile32(RowAcc<D>& st, float (&va)[kQC], flo
             if (bm > st.m && bm > *rm_row) *rm_row = bm;      // publish (bm becomes this warp's running maximum below)
         }
         const float m_new = fmaxf(st.m, bm);
-        if (m_new > st.m) {
+        if (!(VOS_ABL & 4) && m_new > st.m) {
             const float corr = ex2(st.m - m_new);
             st.l *= corr;
 #pragma unroll
@@ -504,6 +606,76 @@ __device__ __forceinline__ void fast_tile32(RowAcc<D>& st, float (&va)[kQC], flo
         }
     }
     const float drc = static_cast<float>(dn) * inv_w;
+    if constexpr (!kWide) {
+        // ---- Horner path (PriorConst::chain_always holds for every reference of the frame)
+        const float neg_m = -st.m;
+        const float2 s2 = make_float2(scale2, scale2);
+        const float2 nm2 = make_float2(neg_m, neg_m);
+        const uint32_t cB = __shfl_sync(full, cls_lane, kQC);
+        const uint32_t sameB = __ballot_sync(full, cls_lane == cB) >> kQC;
+        const bool simple = (VOS_ABL & 8) || (jw >= 2 * kQC && (same32 & 0xffffu) == 0xffffu && sameB == 0xffffu);   // warp-uniform
+        float a0, b0;
+        quad_coeffs(drc, bx, inv_w, pc.coef, 0.f, a0, b0);
+        const float a1 = fmaf(16.f, b0, fmaf(256.f, pc.gamma, a0)), b1 = fmaf(32.f, pc.gamma, b0);   // the same parabola at column 16
+        float2 l2 = make_float2(0.f, 0.f);
+        if (simple) {
+            // no image-row wrap inside the 32 columns and one class per 16-column half (the common case): the exponentials
+            // are consumed as they leave the MUFU, two independent chains
+            HornerStep ha, hb;
+            if (VOS_ABL & 32) { ha.R = hb.R = make_float2(a0, b0); ha.qk = hb.qk = a1; ha.h = hb.h = b1; }
+            else { ha = horner_init(a0, b0, pc); hb = horner_init(a1, b1, pc); }
+            const float2 K8i = make_float2(pc.k8inv, pc.k8inv);
+            float2 Sa = make_float2(0.f, 0.f), Sb = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = kQC / 2 - 1; k >= 0; --k) {
+                const float2 ea = ffma2(make_float2(va[2 * k], va[2 * k + 1]), s2, nm2);
+                const float2 eb = ffma2(make_float2(vb[2 * k], vb[2 * k + 1]), s2, nm2);
+                const float2 pa = (VOS_ABL & 1) ? ea : (kPolyEvery && k % kPolyEvery == kPolyEvery - 1) ? ex2_poly2(ea) : make_float2(ex2(ea.x), ex2(ea.y));
+                const float2 pb = (VOS_ABL & 1) ? eb : (kPolyEvery && k % kPolyEvery == 1 % kPolyEvery) ? ex2_poly2(eb) : make_float2(ex2(eb.x), ex2(eb.y));
+                if (!(VOS_ABL & 16)) l2 = fadd2(l2, fadd2(pa, pb));
+                if (k == kQC / 2 - 1) {
+                    Sa = pa;
+                    Sb = pb;
+                } else if (VOS_ABL & 2) {
+                    Sa.x = fmaxf(Sa.x, pa.x + pa.y);
+                    Sb.x = fmaxf(Sb.x, pb.x + pb.y);
+                } else {
+                    Sa = ffma2(ha.R, Sa, pa);
+                    Sb = ffma2(hb.R, Sb, pb);
+                    if (k > 0) {
+                        ha.R = fmul2(ha.R, K8i);
+                        hb.R = fmul2(hb.R, K8i);
+                    }
+                }
+            }
+            st.l += l2.x + l2.y;
+            const float ta = (VOS_ABL & 32) ? Sa.x + Sa.y + ha.R.x : horner_finish(ha, Sa), tb = (VOS_ABL & 32) ? Sb.x + Sb.y + hb.R.y : horner_finish(hb, Sb);
+            if (cls0 == cB) {
+                add_to_class<D>(st, static_cast<int>(cls0), ta + tb);
+            } else {
+                add_to_class<D>(st, static_cast<int>(cls0), ta);
+                add_to_class<D>(st, static_cast<int>(cB), tb);
+            }
+            return;
+        }
+        // an image-row wrap or a class boundary inside the 32 columns: exponentials first (kept in va / vb), then one masked
+        // Horner pass per (image row, class) present in each half
+#pragma unroll
+        for (int j = 0; j < kQC; j += 2) {
+            const float2 ea = ffma2(make_float2(va[j], va[j + 1]), s2, nm2);
+            const float2 eb = ffma2(make_float2(vb[j], vb[j + 1]), s2, nm2);
+            const float2 pa = make_float2(ex2(ea.x), ex2(ea.y)), pb = make_float2(ex2(eb.x), ex2(eb.y));
+            l2 = fadd2(l2, fadd2(pa, pb));
+            va[j] = pa.x; va[j + 1] = pa.y;
+            vb[j] = pb.x; vb[j + 1] = pb.y;
+        }
+        st.l += l2.x + l2.y;
+        horner_general16<D>(st, va, cls_lane, 0, jw, drc, bx, pc, inv_w, w_lowres);
+        // the second half starts 16 pixels further: on the next image row if the wrap lies in the first half
+        horner_general16<D>(st, vb, cls_lane, kQC, jw > kQC ? jw - kQC : kQC, static_cast<float>(dn + kQC) * inv_w,
+                            bx + static_cast<float>(kQC) - (jw <= kQC ? w_lowres : 0.f), pc, inv_w, w_lowres);
+        return;
+    }
     float ta, tb, sa, sb;           // step sums (of v[]) and the factors still missing from them
     bool direct = false;            // evaluate both halves directly (recurrence unsafe somewhere in the warp)
     bool far_a = false, far_b = false;
@@ -688,7 +860,7 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                             nxt = cls_p + ((jn >= dec.tpf ? jn - dec.tpf : jn) - jp) * kTile;
                         }
                     }
-                    if (nt + 1 < n1) cls_next = __ldg(nxt);
+                    if (!(VOS_ABL & 128) && nt + 1 < n1) cls_next = __ldg(nxt);
                 }
                 const uint32_t valid32 = (jp == dec.tpf - 1) ? ragged : full;
                 mbar_wait_s(pp.acc_full + 8 * buf, aphase);
@@ -696,10 +868,15 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                 const uint32_t taddr = pp.tmem_base + lane_base + buf * kTile + sub * 32;
                 const uint32_t cls0 = __shfl_sync(full, cls_lane, 0);
                 const uint32_t same32 = __ballot_sync(full, cls_lane == cls0);
-                if (valid32 == full && (kWide || pc.chain_always) && prm.dbg == 0) {
+                if (valid32 == full && (kWide || pc.chain_always) && !VOS_DBG_ANY(prm)) {
                     float va[kQC], vb[kQC];
-                    tmem_ld_32x32b_x16(taddr, va);
-                    tmem_ld_32x32b_x16(taddr + kQC, vb);
+                    if (VOS_ABL & 64) {
+#pragma unroll
+                        for (int i = 0; i < kQC; ++i) { va[i] = static_cast<float>(nt + i) * inv_w; vb[i] = static_cast<float>(nt - i) * inv_w; }
+                    } else {
+                        tmem_ld_32x32b_x16(taddr, va);
+                        tmem_ld_32x32b_x16(taddr + kQC, vb);
+                    }
                     tmem_ld_wait();
                     tc_fence_before_sync();
                     __syncwarp();
@@ -710,7 +887,7 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
 #pragma unroll 1
                 for (int q = 0; q < 2; ++q) {
                     float v[kQC];
-                    if (prm.dbg & 32) {
+                    if (VOS_DBG(prm, 32)) {
 #pragma unroll
                         for (int i = 0; i < kQC; ++i) v[i] = 0.f;
                     } else {
@@ -730,13 +907,13 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                     xq += kQC;
                     if (xq >= W) xq -= W;
                     if (valid == 0u) continue;                       // beyond the frame's last pixel
-                    if (prm.dbg & 1) { st.l += v[0]; continue; }
+                    if (VOS_DBG(prm, 1)) { st.l += v[0]; continue; }
                     if (valid != 0xffffu) {
 #pragma unroll
                         for (int i = 0; i < kQC; ++i)
                             if (!((valid >> i) & 1u)) v[i] = -INFINITY;
                     }
-                    if (!(prm.dbg & 8)) update_max<D>(st, v, scale2);
+                    if (!VOS_DBG(prm, 8)) update_max<D>(st, v, scale2);
                     float sum, scale;
                     bool fast = jw >= kQC && valid == 0xffffu;
                     float a0, b0, sh;
@@ -754,8 +931,8 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                             fast = __all_sync(full, !live || chain_ok);
                         }
                     }
-                    if (prm.dbg & 4) { a0 = 0.f; b0 = 0.f; sh = 0.f; live = true; fast = true; }
-                    if (prm.dbg & 16) {
+                    if (VOS_DBG(prm, 4)) { a0 = 0.f; b0 = 0.f; sh = 0.f; live = true; fast = true; }
+                    if (VOS_DBG(prm, 16)) {
                         float l = 0.f;
 #pragma unroll
                         for (int i = 0; i < kQC; ++i) l += ex2(fmaf(v[i], scale2, -st.m));
@@ -764,7 +941,7 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                     if (fast) scale = step16_chain<D>(st, v, a0, b0, sh, live, pc, scale2, sum);
                     else scale = step16_direct<D>(st, v, drc, bx, jw, valid, pc, inv_w, scale2, w_f, sum);
                     // ---- label gather: add each column's weight to its class (class bytes are warp-uniform per column)
-                    if (prm.dbg & 2) { st.acc[0] += sum * scale; continue; }
+                    if (VOS_DBG(prm, 2)) { st.acc[0] += sum * scale; continue; }
                     uint32_t c = cls0, mk = same32 & 0xffffu;
                     if (q == 1 || valid != 0xffffu) {
                         c = __shfl_sync(full, cls_lane, lane_shift + __ffs(valid) - 1);

@@ -16,14 +16,10 @@
 //   vos_upsample_mask : stride-8 class map -> full-resolution uint8 mask (ATen legacy 'nearest').
 #pragma once
 #include "affinity_idx.cuh"
+#include "topk_params.h"
 
 namespace vosk {
 
-constexpr int kTopkGroup = 2;                  // chunks per pipeline stage (32 KiB)
-constexpr int kTopkMax = 64;                   // largest supported k
-constexpr int kTopkK16 = 8;                    // k <= this: 16 epilogue warps, 36 slots per thread
-constexpr int kTopkK8 = 24;                    // k <= this:  8 epilogue warps, 64 slots per thread; larger k: 4 warps, 112 slots
-constexpr int kTopkMaxCand = 2048;             // candidates merged per target pixel by the finish kernel (lists x k)
 
 // Shape of the top-k epilogue: kSub column groups per tile, 4 * kSub warps, one thread = one target pixel x 128 / kSub
 // columns with its own buffer.  kSub = 1: 112 slots (any k <= 64), one warp per scheduler -- latency bound
@@ -227,19 +223,7 @@ vos_affinity_topk(const __grid_constant__ CUtensorMap tmap_hi, const __grid_cons
 // -------------------------------------------------------------------------------------------
 // Finish: one warp per target pixel.
 // -------------------------------------------------------------------------------------------
-struct TopkFinishParams {
-    MergeParams mp;               // geometry + outputs shared with vos_merge_writeback
-    int32_t topk;
-    int32_t ref_slot[32];
-    float ref_coef[32];           // log2(e) / sigma^2 ; 0 = no prior
-    const uint32_t* cand_key;     // [grid * max_segs][128][kTopkMax]
-    const int32_t* cand_idx;
-    const int32_t* cand_cnt;      // [grid * max_segs][128]
-    int32_t* out_topk_idx;        // (P, topk) int32 or null; value-descending, -1 where fewer than k references exist
-};
 
-constexpr int kFinishWarps = 4;
-constexpr int kFinishSmem = kFinishWarps * (kTopkMaxCand * 8 + kTopkMax * 8);
 
 __global__ void __launch_bounds__(kFinishWarps * 32) vos_topk_finish(const TopkFinishParams fp) {
     extern __shared__ uint32_t fsm[];

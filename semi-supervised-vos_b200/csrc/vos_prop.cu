@@ -17,8 +17,9 @@
 
 #include "decompose.h"
 #include "kernels.cuh"
-#include "affinity_idx.cuh"
-#include "affinity_topk.cuh"
+#include "side_kernels.cuh"
+#include "launch.h"
+#include "topk_params.h"
 
 static_assert(VOSPROP_PREC_SPLIT3 == vosk::kFmtSplit && VOSPROP_PREC_F16 == vosk::kFmtF16 && VOSPROP_PREC_BF16 == vosk::kFmtBF16,
               "precision enum and ring formats must coincide");
@@ -87,20 +88,7 @@ struct vosprop_engine {
 };
 
 namespace {
-// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream is still running;
-// every kernel launched this way executes griddepcontrol.wait (vosptx::pdl_wait) before it touches memory the
-// predecessor writes, and griddepcontrol.launch_dependents at its start.  This hides the ~5 us launch gaps between the
-// three kernels of a frame (append -> fused affinity -> merge), 6 % of a 480p frame.
-template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
-}
+using vosk::launch_pdl;
 
 struct TimedLaunch {   // RAII: records an event pair around one kernel launch when timing is on
     vosprop_engine* e; cudaStream_t st; bool on;
@@ -136,16 +124,22 @@ int encode_maps(vosprop_engine* e) {
     return VOSPROP_OK;
 }
 
-template <int D>
-int launch_affinity(vosprop_engine* e, const vosk::AffinityParams& prm, int grid, int kernel, cudaStream_t st) {
+int dispatch_affinity(vosprop_engine* e, const vosk::AffinityParams& prm, int grid, int kernel, cudaStream_t st) {
+    // smallest instantiated class capacity >= d
+    static const int caps[] = {2, 3, 4, 6, 8, 11, 14, vosk::kMaxClasses};
+    int D = vosk::kMaxClasses;
+    for (int c : caps)
+        if (e->d <= c) { D = c; break; }
+    cudaError_t ce;
     if (kernel == VOSPROP_KERNEL_TC) {
         // same bound as vosk::prior_const: is the prior recurrence safe for every reference of this step?
         bool wide = false;
         const float inv_w = prm.inv_w, w = static_cast<float>(prm.w_lowres), h = static_cast<float>((prm.n_pixels + prm.w_lowres - 1) / prm.w_lowres);
         for (int r = 0; r < prm.n_refs; ++r) {
             const float coef = prm.ref_coef[r], gamma = -coef * (inv_w * inv_w + 1.0f);
-            wide = wide || !(30.f * coef * (h * inv_w + w) - 225.f * gamma < 100.f);
+            wide = wide || !(30.f * coef * (h * inv_w + w + 16.f) - 225.f * gamma < 100.f);
         }
+        if (D > vosk::kMetaClasses) wide = true;      // 15..24 classes: only the per-tile-tested form is instantiated
         const bool split = prm.feat_fmt == vosk::kFmtSplit;
         const bool skip = e->block_skip && !wide;
         vosk::AffinityParams prm_k = prm;
@@ -157,37 +151,11 @@ int launch_affinity(vosprop_engine* e, const vosk::AffinityParams& prm, int grid
             while (s < tpf && gcd(s, tpf) != 1) ++s;
             prm_k.tile_stride = s < tpf ? s : 1;
         }
-        void (*kern)(CUtensorMap, CUtensorMap, vosk::AffinityParams) =
-            split ? (wide ? vosk::vos_affinity_idx<D, true, true> : skip ? vosk::vos_affinity_idx<D, true, false, true> : vosk::vos_affinity_idx<D, true, false>)
-                  : (wide ? vosk::vos_affinity_idx<D, false, true> : skip ? vosk::vos_affinity_idx<D, false, false, true> : vosk::vos_affinity_idx<D, false, false>);
-        VOS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kIdxSmem));
-        VOS_CUDA(launch_pdl(kern, grid, vosk::kIdxThreads, vosk::kIdxSmem, st, e->tmap_hi, e->tmap_lo, prm_k));
-    } else if (kernel == VOSPROP_KERNEL_TC_DENSE) {
-        VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_tc<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kSmemTc));
-        vosk::vos_affinity_tc<D><<<grid, vosk::kTcThreads, vosk::kSmemTc, st>>>(e->tmap_hi, e->tmap_lo, prm);
+        ce = vosk::launch_affinity_idx(D, split, wide, skip, grid, st, e->tmap_hi, e->tmap_lo, prm_k);
     } else {
-        VOS_CUDA(cudaFuncSetAttribute(vosk::vos_affinity_simt<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kSmemSimt));
-        vosk::vos_affinity_simt<D><<<grid, vosk::kSimtThreads, vosk::kSmemSimt, st>>>(prm);
+        ce = vosk::launch_affinity_dense(D, kernel == VOSPROP_KERNEL_SIMT, grid, st, e->tmap_hi, e->tmap_lo, prm);
     }
-    VOS_CUDA(cudaGetLastError());
-    return VOSPROP_OK;
-}
-
-int dispatch_affinity(vosprop_engine* e, const vosk::AffinityParams& prm, int grid, int kernel, cudaStream_t st) {
-    const int d = e->d;
-    if (d <= 2) return launch_affinity<2>(e, prm, grid, kernel, st);
-    if (d <= 3) return launch_affinity<3>(e, prm, grid, kernel, st);
-    if (d <= 4) return launch_affinity<4>(e, prm, grid, kernel, st);
-    if (d <= 6) return launch_affinity<6>(e, prm, grid, kernel, st);
-    if (d <= 8) return launch_affinity<8>(e, prm, grid, kernel, st);
-    if (d <= 11) return launch_affinity<11>(e, prm, grid, kernel, st);
-    if (d <= vosk::kMetaClasses) return launch_affinity<14>(e, prm, grid, kernel, st);
-    // 15..24 classes: index-label kernel only (vosprop_propagate has checked that)
-    const bool split = prm.feat_fmt == vosk::kFmtSplit;
-    void (*kern)(CUtensorMap, CUtensorMap, vosk::AffinityParams) =
-        split ? vosk::vos_affinity_idx<vosk::kMaxClasses, true, true> : vosk::vos_affinity_idx<vosk::kMaxClasses, false, true>;
-    VOS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kIdxSmem));
-    VOS_CUDA(launch_pdl(kern, grid, vosk::kIdxThreads, vosk::kIdxSmem, st, e->tmap_hi, e->tmap_lo, prm));
+    if (ce != cudaSuccess) return fail(VOSPROP_ERR_CUDA, "affinity kernel launch failed: %s", cudaGetErrorString(ce));
     VOS_CUDA(cudaGetLastError());
     return VOSPROP_OK;
 }
@@ -233,15 +201,7 @@ int propagate_topk(vosprop_engine* e, const vosprop_step* s, vosk::AffinityParam
     ap.cand_key = e->cand_key; ap.cand_idx = e->cand_idx; ap.cand_cnt = e->cand_cnt;
     {
         TimedLaunch timed(e, VOSPROP_T_AFFINITY, st);
-        const bool split = ap.feat_fmt == vosk::kFmtSplit;
-        void (*kern)(CUtensorMap, CUtensorMap, vosk::AffinityParams) =
-            n_sub == 4 ? (split ? vosk::vos_affinity_topk<true, 4> : vosk::vos_affinity_topk<false, 4>)
-          : n_sub == 2 ? (split ? vosk::vos_affinity_topk<true, 2> : vosk::vos_affinity_topk<false, 2>)
-                       : (split ? vosk::vos_affinity_topk<true, 1> : vosk::vos_affinity_topk<false, 1>);
-        const int smem = n_sub == 4 ? vosk::TopkCfg<4>::kSmem : (n_sub == 2 ? vosk::TopkCfg<2>::kSmem : vosk::TopkCfg<1>::kSmem);
-        const int threads = n_sub == 4 ? vosk::TopkCfg<4>::kThreads : (n_sub == 2 ? vosk::TopkCfg<2>::kThreads : vosk::TopkCfg<1>::kThreads);
-        VOS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        kern<<<dec.grid, threads, smem, st>>>(e->tmap_hi, e->tmap_lo, ap);
+        VOS_CUDA(vosk::launch_affinity_topk(ap.feat_fmt == vosk::kFmtSplit, n_sub, dec.grid, st, e->tmap_hi, e->tmap_lo, ap));
         VOS_CUDA(cudaGetLastError());
     }
     if (s->record_event) VOS_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->record_event), st));
@@ -261,12 +221,9 @@ int propagate_topk(vosprop_engine* e, const vosprop_step* s, vosk::AffinityParam
     fp.out_topk_idx = s->out_topk_idx;
     {
         TimedLaunch timed(e, VOSPROP_T_MERGE, st);
-        VOS_CUDA(cudaFuncSetAttribute(vosk::vos_topk_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, vosk::kFinishSmem));
-        vosk::vos_topk_finish<<<(e->P + vosk::kFinishWarps - 1) / vosk::kFinishWarps, vosk::kFinishWarps * 32, vosk::kFinishSmem, st>>>(fp);
-        VOS_CUDA(cudaGetLastError());
+        VOS_CUDA(vosk::launch_topk_finish(fp, st));
         if (s->out_mask_fullres) {
-            vosk::vos_upsample_mask<<<e->H, 256, 0, st>>>(mp.out_mask_lowres, s->out_mask_fullres, e->H_d, e->W_d, e->H, e->W);
-            VOS_CUDA(cudaGetLastError());
+            VOS_CUDA(vosk::launch_upsample_mask(mp.out_mask_lowres, s->out_mask_fullres, e->H_d, e->W_d, e->H, e->W, st));
             e->launches++;
         }
     }
@@ -556,6 +513,7 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
         // stream-ordered, so a host that runs clips ahead of the device never races with it)
         int32_t* dev = e->tables + static_cast<size_t>(s->n_refs) * e->table_stride;
         if (!e->table_valid[s->n_refs]) {
+            mp.tables_fresh = 1;
             vosk::vos_decomp_tables<<<1, 256, 0, st>>>(dev, e->P, s->n_refs, e->num_sms);
             VOS_CUDA(cudaGetLastError());
             e->table_valid[s->n_refs] = 1;

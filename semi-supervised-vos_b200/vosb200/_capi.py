@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 MAX_REFS = 32
@@ -16,7 +17,8 @@ PREC_SPLIT3, PREC_F16, PREC_BF16 = 0, 1, 2
 ABI_VERSION = 3
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4
 
-LIB_PATH = Path(__file__).resolve().parent.parent / 'csrc' / 'libvosprop.so'
+# VOS_LIB_NAME selects a variant build of the same sources (vosb200/build.py); the product is libvosprop.so
+LIB_PATH = Path(__file__).resolve().parent.parent / 'csrc' / os.environ.get('VOS_LIB_NAME', 'libvosprop.so')
 
 
 class Config(C.Structure):
