@@ -30,18 +30,15 @@
 #define VOS_CLK() 0ll
 #endif
 
-// Timing experiments on the fast tile path (tools/gpu_ab.sh builds variants with -DVOS_ABL=<bits>; results are WRONG with
-// any bit set): 1 no MUFU for the logits, 2 no Horner chain, 4 no running-max update, 8 every block takes the simple path,
-// 16 no denominator sum, 32 no chain set-up / finish, 64 no TMEM loads, 128 no class bytes.
-#ifndef VOS_ABL
-#define VOS_ABL 0
-#endif
 
 namespace vosk {
 
 constexpr int kIdxEpiWarps = 16;     // 4 per scheduler: each owns 32 TMEM lanes x 32 logit columns of a tile
 constexpr int kIdxEpiThreads = kIdxEpiWarps * 32;
 constexpr int kIdxThreads = 64 + kIdxEpiThreads;   // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue
+// (A 20-warp layout with setmaxnreg -- role warpgroup down to 24..48 registers, epilogue warpgroups up to 104..112 -- was
+// built in round 2: ptxas uses at most 100 registers in the epilogue even when allowed 168, so the 96 of this layout cost
+// nothing, while the role warps spill below 56.  Not kept.)
 constexpr int kIdxRingChunks = 12;   // 12 x 16 KiB of reference chunks in flight, grouped into stages (IdxCfg)
 constexpr int kIdxMaxAccBufs = 3;
 constexpr int kIdxRowMaxBytes = 4 * kTile * 4;   // block skipping: 4 segment-parity slots x 128 rows of shared running maxima
@@ -332,12 +329,8 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, float (&v)[16
 }
 
 constexpr int kQC = 16;   // columns per epilogue step
-#ifndef VOS_POLY_EVERY
-#define VOS_POLY_EVERY 0
-#endif
-constexpr int kPolyEvery = VOS_POLY_EVERY;   // fast tile path: 1 of kPolyEvery column pairs uses the polynomial exp2 (0: none).
-// Measured (480p, R = 9, F16): 0 -> 225 us, 4 -> 234 us, 2 -> 242 us per launch: the epilogue warps are bound by their own
-// instruction latency, not by the MUFU pipe, so trading one MUFU for ~7 FMA/ALU instructions loses.  Kept for the record.
+// (Moving 1/4 or 1/2 of the exponentials from the MUFU to the FMA pipe -- vosptx::ex2_poly2, the FlashAttention-4 trick -- was
+// measured at 480p, R = 9, F16: 225 -> 234 / 242 us per launch.  The epilogue is bound by its instruction count, not by the MUFU.)
 
 __device__ __forceinline__ float max16(const float (&v)[kQC]) {
     const float a = fmax3(v[0], v[1], v[2]), b = fmax3(v[3], v[4], v[5]), c = fmax3(v[6], v[7], v[8]);
@@ -562,16 +555,112 @@ __device__ __forceinline__ void horner_general16(RowAcc<D>& st, const float (&p)
     }
 }
 
-// ---- Fast tile path: this warp's 32 columns are all real and the recurrence is safe for the whole frame
-// (PriorConst::chain_always).  Per-step bookkeeping (validity masks, path selection) is decided once per tile by the
-// caller; the common case (no image-row wrap inside the 32 columns) is straight-line code with two independent
-// 16-column chains.  The first capture of the single-pass kernel showed every epilogue warp latency-bound on that
-// bookkeeping (~9 cycles per instruction, 4 warps per scheduler), not on MUFU or issue slots.
-// jw = first of the 32 columns that lies on the next image row (>= 32: none).
-template <int D, bool kWide, bool kSkip>
-__device__ __forceinline__ void fast_tile32(RowAcc<D>& st, float (&va)[kQC], float (&vb)[kQC], uint32_t cls_lane, uint32_t cls0,
-                                            uint32_t same32, int dn, float bx, int jw, const PriorConst& pc, float inv_w,
-                                            float scale2, float w_lowres, uint32_t& probe, volatile float* rm_row, bool row_real) {
+// ---- One 16-column half of a tile that is not all-simple (fast_tile32, !kWide): p[] holds the exponentials.
+// The columns of a half form GROUPS of equal (image row, class).  One group: a single Horner chain.  Two groups (an
+// image-row wrap inside the half -- every 128-pixel tile of a 107-pixel-wide map has one -- or a class boundary): both
+// chains run side by side over all 16 columns, each fed the exponentials of its own columns (P_B = P - P_A is exact: one
+// of the two is 0), each normalised to its own parabola's (virtual) column 0 -- 5 packed operations per column pair
+// instead of two complete masked passes through the loops of horner_general16, which stays as the fallback for three
+// or more groups.  The per-scheduler instruction count is what bounds this kernel (profiles/README.md, round 2: with
+// every tile forced down the simple path the launch took 187 instead of 236 us), and before this path existed a tile
+// with a wrap cost 2.3 x a simple one.
+// jwh: first column of the half on the next image row (>= 16: none; never 0).  (drc, bx): geometry of column 0.
+template <int D>
+__device__ __forceinline__ void horner_half16(RowAcc<D>& st, const float (&p)[kQC], uint32_t cls_lane, int lane_shift, int jwh,
+                                              float drc, float bx, const PriorConst& pc, float inv_w, float w_lowres,
+                                              uint32_t c0, uint32_t m0) {
+    // c0: class of the half's column 0; m0: the half's columns of that class (both warp-uniform, from the caller's ballots)
+    const uint32_t full = 0xffffffffu;
+    const float2 K8i = make_float2(pc.k8inv, pc.k8inv);
+    const uint32_t row0 = jwh >= kQC ? 0xffffu : ((1u << jwh) - 1u);      // columns on the image row of column 0
+    const uint32_t gA = m0 & row0;                                          // group of column 0
+    const uint32_t rest = 0xffffu & ~gA;
+    float aA, bA;
+    quad_coeffs(drc, bx, inv_w, pc.coef, 0.f, aA, bA);
+    HornerStep hA = horner_init(aA, bA, pc);
+    if (rest == 0u) {                                                      // ---- one group
+        float2 S = make_float2(p[14], p[15]);
+#pragma unroll
+        for (int k = 6; k >= 0; --k) {
+            S = ffma2(hA.R, S, make_float2(p[2 * k], p[2 * k + 1]));
+            if (k > 0) hA.R = fmul2(hA.R, K8i);
+        }
+        add_to_class<D>(st, static_cast<int>(c0), horner_finish(hA, S));
+        return;
+    }
+    const int j1 = __ffs(rest) - 1;                                        // first column outside group A
+    const uint32_t c1 = __shfl_sync(full, cls_lane, lane_shift + j1);
+    const bool next_row = j1 >= jwh;
+    const uint32_t gB = (__ballot_sync(full, cls_lane == c1) >> lane_shift) & (next_row ? 0xffffu & ~row0 : row0);
+    if (gB != rest) {                                                      // ---- three or more groups (rare)
+        horner_general16<D>(st, p, cls_lane, lane_shift, jwh, drc, bx, pc, inv_w, w_lowres);
+        return;
+    }
+    // ---- two groups: both chains side by side
+    const float2 neg1 = make_float2(-1.f, -1.f);
+    float2 SA = make_float2(0.f, 0.f), SB = make_float2(0.f, 0.f);
+    float tA, tB;
+    if (!next_row) {
+        // a class boundary on one image row: one parabola, the chains share their multipliers
+#pragma unroll
+        for (int k = kQC / 2 - 1; k >= 0; --k) {
+            const float2 P = make_float2(p[2 * k], p[2 * k + 1]);
+            const float2 PA = make_float2(((gA >> (2 * k)) & 1u) ? P.x : 0.f, ((gA >> (2 * k + 1)) & 1u) ? P.y : 0.f);
+            const float2 PB = ffma2(PA, neg1, P);
+            if (k == kQC / 2 - 1) {
+                SA = PA;
+                SB = PB;
+            } else {
+                SA = ffma2(hA.R, SA, PA);
+                SB = ffma2(hA.R, SB, PB);
+                if (k > 0) hA.R = fmul2(hA.R, K8i);
+            }
+        }
+        tA = horner_finish(hA, SA);
+        tB = horner_finish(hA, SB);
+    } else {
+        // an image-row wrap: group B lies on the next row (x jumps back by W) and has its own parabola
+        float aB, bB;
+        quad_coeffs(drc, bx - w_lowres, inv_w, pc.coef, 0.f, aB, bB);
+        HornerStep hB = horner_init(aB, bB, pc);
+#pragma unroll
+        for (int k = kQC / 2 - 1; k >= 0; --k) {
+            const float2 P = make_float2(p[2 * k], p[2 * k + 1]);
+            const float2 PA = make_float2(((gA >> (2 * k)) & 1u) ? P.x : 0.f, ((gA >> (2 * k + 1)) & 1u) ? P.y : 0.f);
+            const float2 PB = ffma2(PA, neg1, P);
+            if (k == kQC / 2 - 1) {
+                SA = PA;
+                SB = PB;
+            } else {
+                SA = ffma2(hA.R, SA, PA);
+                SB = ffma2(hB.R, SB, PB);
+                if (k > 0) {
+                    hA.R = fmul2(hA.R, K8i);
+                    hB.R = fmul2(hB.R, K8i);
+                }
+            }
+        }
+        tA = horner_finish(hA, SA);
+        tB = horner_finish(hB, SB);
+    }
+    if (c0 == c1) {
+        add_to_class<D>(st, static_cast<int>(c0), tA + tB);
+    } else {
+        add_to_class<D>(st, static_cast<int>(c0), tA);
+        add_to_class<D>(st, static_cast<int>(c1), tB);
+    }
+}
+
+// ---- 480p product path (!kWide), phase 1: running maximum, exponentials IN PLACE (va / vb <- 2^(s*scale2 - m)), softmax
+// denominator.  Returns false for a dead block: nothing to add (kSkip).
+// While one warp of a scheduler sits in this MUFU-bound phase the other three run their FMA-bound Horner chains (phase 2).
+// (A "lazy maximum" -- no maximum tree; the reference value m follows the tile sums, tiles whose exponentials leave the
+// fp32 range are reloaded from TMEM and redone exactly -- was built and measured in round 2: 6 % fewer instructions, the
+// same launch time, because the accumulator buffer can be handed back to the MMA warp only after the tile has been
+// judged and the epilogue warps then wait for the tensor pipe.  Not kept; profiles/README.md.)
+template <int D, bool kSkip>
+__device__ __forceinline__ bool tile_exps32(RowAcc<D>& st, float (&va)[kQC], float (&vb)[kQC], float scale2, uint32_t& probe,
+                                            volatile float* rm_row, bool row_real) {
     const uint32_t full = 0xffffffffu;
     {
         const float bm = fmaxf(max16(va), max16(vb)) * scale2;
@@ -592,12 +681,93 @@ __device__ __forceinline__ void fast_tile32(RowAcc<D>& st, float (&va)[kQC], flo
                 const bool dead = __all_sync(full, !row_real || bm - bound < -127.f);
                 const uint32_t window = dead ? 64u : max(probe >> 16, 1u) - 1u;
                 probe = (probe & 0xffffu) | (window << 16);
-                if (dead) return;
+                if (dead) return false;
             }
             if (bm > st.m && bm > *rm_row) *rm_row = bm;      // publish (bm becomes this warp's running maximum below)
         }
         const float m_new = fmaxf(st.m, bm);
-        if (!(VOS_ABL & 4) && m_new > st.m) {
+        if (m_new > st.m) {
+            const float corr = ex2(st.m - m_new);
+            st.l *= corr;
+#pragma unroll
+            for (int c = 0; c < D; ++c) st.acc[c] *= corr;
+            st.m = m_new;
+        }
+    }
+    const float neg_m = -st.m;
+    const float2 s2 = make_float2(scale2, scale2);
+    const float2 nm2 = make_float2(neg_m, neg_m);
+    float2 l2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < kQC; j += 2) {
+        const float2 ea = ffma2(make_float2(va[j], va[j + 1]), s2, nm2);
+        const float2 eb = ffma2(make_float2(vb[j], vb[j + 1]), s2, nm2);
+        const float2 pa = make_float2(ex2(ea.x), ex2(ea.y)), pb = make_float2(ex2(eb.x), ex2(eb.y));
+        l2 = fadd2(l2, fadd2(pa, pb));
+        va[j] = pa.x; va[j + 1] = pa.y;
+        vb[j] = pb.x; vb[j + 1] = pb.y;
+    }
+    st.l += l2.x + l2.y;
+    return true;
+}
+
+// ---- phase 2: prior-weighted class sums of the 32 exponentials (Horner form, PriorConst::chain_always holds for every
+// reference of the frame).
+// jw = first of the 32 columns that lies on the next image row (>= 32: none).
+template <int D>
+__device__ __forceinline__ void tile_prior32(RowAcc<D>& st, const float (&va)[kQC], const float (&vb)[kQC], uint32_t cls_lane,
+                                             uint32_t cls0, uint32_t same32, int dn, float bx, int jw, const PriorConst& pc,
+                                             float inv_w, float w_lowres) {
+    const uint32_t full = 0xffffffffu;
+    const float drc = static_cast<float>(dn) * inv_w;
+    const uint32_t cB = __shfl_sync(full, cls_lane, kQC);
+    const uint32_t sameB = __ballot_sync(full, cls_lane == cB) >> kQC;
+    const bool simple = jw >= 2 * kQC && (same32 & 0xffffu) == 0xffffu && sameB == 0xffffu;   // warp-uniform
+    if (simple) {
+        // no image-row wrap inside the 32 columns and one class per 16-column half (the common case): two independent chains
+        float a0, b0;
+        quad_coeffs(drc, bx, inv_w, pc.coef, 0.f, a0, b0);
+        const float a1 = fmaf(16.f, b0, fmaf(256.f, pc.gamma, a0)), b1 = fmaf(32.f, pc.gamma, b0);   // the same parabola at column 16
+        HornerStep ha = horner_init(a0, b0, pc), hb = horner_init(a1, b1, pc);
+        const float2 K8i = make_float2(pc.k8inv, pc.k8inv);
+        float2 Sa = make_float2(va[kQC - 2], va[kQC - 1]), Sb = make_float2(vb[kQC - 2], vb[kQC - 1]);
+#pragma unroll
+        for (int k = kQC / 2 - 2; k >= 0; --k) {
+            Sa = ffma2(ha.R, Sa, make_float2(va[2 * k], va[2 * k + 1]));
+            Sb = ffma2(hb.R, Sb, make_float2(vb[2 * k], vb[2 * k + 1]));
+            if (k > 0) {
+                ha.R = fmul2(ha.R, K8i);
+                hb.R = fmul2(hb.R, K8i);
+            }
+        }
+        const float ta = horner_finish(ha, Sa), tb = horner_finish(hb, Sb);
+        if (cls0 == cB) {
+            add_to_class<D>(st, static_cast<int>(cls0), ta + tb);
+        } else {
+            add_to_class<D>(st, static_cast<int>(cls0), ta);
+            add_to_class<D>(st, static_cast<int>(cB), tb);
+        }
+    } else {
+        // an image-row wrap or a class boundary inside the 32 columns: each half by its groups of equal (image row, class)
+        horner_half16<D>(st, va, cls_lane, 0, jw, drc, bx, pc, inv_w, w_lowres, cls0, same32 & 0xffffu);
+        // the second half starts 16 pixels further: on the next image row if the wrap lies in the first half
+        horner_half16<D>(st, vb, cls_lane, kQC, jw > kQC ? jw - kQC : kQC, static_cast<float>(dn + kQC) * inv_w,
+                         bx + static_cast<float>(kQC) - (jw <= kQC ? w_lowres : 0.f), pc, inv_w, w_lowres, cB, sameB);
+    }
+}
+
+// ---- Fast tile path of the wide instantiation (kWide: 1080p / narrow sigma / 15..24 classes): forward recurrence with
+// per-tile safety tests.  This warp's 32 columns are all real.  Per-step bookkeeping (validity masks, path selection) is
+// decided once per tile by the caller.  jw = first of the 32 columns that lies on the next image row (>= 32: none).
+template <int D>
+__device__ __forceinline__ void fast_tile32_wide(RowAcc<D>& st, float (&va)[kQC], float (&vb)[kQC], uint32_t cls_lane, uint32_t cls0,
+                                                 uint32_t same32, int dn, float bx, int jw, const PriorConst& pc, float inv_w,
+                                                 float scale2, float w_lowres) {
+    constexpr bool kWide = true;
+    const uint32_t full = 0xffffffffu;
+    {
+        const float m_new = fmaxf(st.m, fmaxf(max16(va), max16(vb)) * scale2);
+        if (m_new > st.m) {
             const float corr = ex2(st.m - m_new);
             st.l *= corr;
 #pragma unroll
@@ -606,76 +776,6 @@ __device__ __forceinline__ void fast_tile32(RowAcc<D>& st, float (&va)[kQC], flo
         }
     }
     const float drc = static_cast<float>(dn) * inv_w;
-    if constexpr (!kWide) {
-        // ---- Horner path (PriorConst::chain_always holds for every reference of the frame)
-        const float neg_m = -st.m;
-        const float2 s2 = make_float2(scale2, scale2);
-        const float2 nm2 = make_float2(neg_m, neg_m);
-        const uint32_t cB = __shfl_sync(full, cls_lane, kQC);
-        const uint32_t sameB = __ballot_sync(full, cls_lane == cB) >> kQC;
-        const bool simple = (VOS_ABL & 8) || (jw >= 2 * kQC && (same32 & 0xffffu) == 0xffffu && sameB == 0xffffu);   // warp-uniform
-        float a0, b0;
-        quad_coeffs(drc, bx, inv_w, pc.coef, 0.f, a0, b0);
-        const float a1 = fmaf(16.f, b0, fmaf(256.f, pc.gamma, a0)), b1 = fmaf(32.f, pc.gamma, b0);   // the same parabola at column 16
-        float2 l2 = make_float2(0.f, 0.f);
-        if (simple) {
-            // no image-row wrap inside the 32 columns and one class per 16-column half (the common case): the exponentials
-            // are consumed as they leave the MUFU, two independent chains
-            HornerStep ha, hb;
-            if (VOS_ABL & 32) { ha.R = hb.R = make_float2(a0, b0); ha.qk = hb.qk = a1; ha.h = hb.h = b1; }
-            else { ha = horner_init(a0, b0, pc); hb = horner_init(a1, b1, pc); }
-            const float2 K8i = make_float2(pc.k8inv, pc.k8inv);
-            float2 Sa = make_float2(0.f, 0.f), Sb = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int k = kQC / 2 - 1; k >= 0; --k) {
-                const float2 ea = ffma2(make_float2(va[2 * k], va[2 * k + 1]), s2, nm2);
-                const float2 eb = ffma2(make_float2(vb[2 * k], vb[2 * k + 1]), s2, nm2);
-                const float2 pa = (VOS_ABL & 1) ? ea : (kPolyEvery && k % kPolyEvery == kPolyEvery - 1) ? ex2_poly2(ea) : make_float2(ex2(ea.x), ex2(ea.y));
-                const float2 pb = (VOS_ABL & 1) ? eb : (kPolyEvery && k % kPolyEvery == 1 % kPolyEvery) ? ex2_poly2(eb) : make_float2(ex2(eb.x), ex2(eb.y));
-                if (!(VOS_ABL & 16)) l2 = fadd2(l2, fadd2(pa, pb));
-                if (k == kQC / 2 - 1) {
-                    Sa = pa;
-                    Sb = pb;
-                } else if (VOS_ABL & 2) {
-                    Sa.x = fmaxf(Sa.x, pa.x + pa.y);
-                    Sb.x = fmaxf(Sb.x, pb.x + pb.y);
-                } else {
-                    Sa = ffma2(ha.R, Sa, pa);
-                    Sb = ffma2(hb.R, Sb, pb);
-                    if (k > 0) {
-                        ha.R = fmul2(ha.R, K8i);
-                        hb.R = fmul2(hb.R, K8i);
-                    }
-                }
-            }
-            st.l += l2.x + l2.y;
-            const float ta = (VOS_ABL & 32) ? Sa.x + Sa.y + ha.R.x : horner_finish(ha, Sa), tb = (VOS_ABL & 32) ? Sb.x + Sb.y + hb.R.y : horner_finish(hb, Sb);
-            if (cls0 == cB) {
-                add_to_class<D>(st, static_cast<int>(cls0), ta + tb);
-            } else {
-                add_to_class<D>(st, static_cast<int>(cls0), ta);
-                add_to_class<D>(st, static_cast<int>(cB), tb);
-            }
-            return;
-        }
-        // an image-row wrap or a class boundary inside the 32 columns: exponentials first (kept in va / vb), then one masked
-        // Horner pass per (image row, class) present in each half
-#pragma unroll
-        for (int j = 0; j < kQC; j += 2) {
-            const float2 ea = ffma2(make_float2(va[j], va[j + 1]), s2, nm2);
-            const float2 eb = ffma2(make_float2(vb[j], vb[j + 1]), s2, nm2);
-            const float2 pa = make_float2(ex2(ea.x), ex2(ea.y)), pb = make_float2(ex2(eb.x), ex2(eb.y));
-            l2 = fadd2(l2, fadd2(pa, pb));
-            va[j] = pa.x; va[j + 1] = pa.y;
-            vb[j] = pb.x; vb[j + 1] = pb.y;
-        }
-        st.l += l2.x + l2.y;
-        horner_general16<D>(st, va, cls_lane, 0, jw, drc, bx, pc, inv_w, w_lowres);
-        // the second half starts 16 pixels further: on the next image row if the wrap lies in the first half
-        horner_general16<D>(st, vb, cls_lane, kQC, jw > kQC ? jw - kQC : kQC, static_cast<float>(dn + kQC) * inv_w,
-                            bx + static_cast<float>(kQC) - (jw <= kQC ? w_lowres : 0.f), pc, inv_w, w_lowres);
-        return;
-    }
     float ta, tb, sa, sb;           // step sums (of v[]) and the factors still missing from them
     bool direct = false;            // evaluate both halves directly (recurrence unsafe somewhere in the warp)
     bool far_a = false, far_b = false;
@@ -723,10 +823,7 @@ __device__ __forceinline__ void fast_tile32(RowAcc<D>& st, float (&va)[kQC], flo
         for (int j = 0; j < kQC; j += 2) {
             const float2 ea = ffma2(make_float2(va[j], va[j + 1]), s2, nm2);
             const float2 eb = ffma2(make_float2(vb[j], vb[j + 1]), s2, nm2);
-            // every kPolyEvery-th column pair takes its exponentials from the FMA pipe (ex2_poly2): the MUFU is the
-            // busiest pipe of this kernel (58 % in the v10 capture), the FMA pipe has room
-            const float2 pa = (kPolyEvery && (j / 2) % kPolyEvery == kPolyEvery - 1) ? ex2_poly2(ea) : make_float2(ex2(ea.x), ex2(ea.y));
-            const float2 pb = (kPolyEvery && (j / 2) % kPolyEvery == 1 % kPolyEvery) ? ex2_poly2(eb) : make_float2(ex2(eb.x), ex2(eb.y));
+            const float2 pa = make_float2(ex2(ea.x), ex2(ea.y)), pb = make_float2(ex2(eb.x), ex2(eb.y));
             l2 = fadd2(l2, fadd2(pa, pb));
             const float2 wa = fmul2(pa, Ga), wb = fmul2(pb, Gb);
             suma = fadd2(suma, wa);
@@ -775,6 +872,7 @@ __device__ __forceinline__ void fast_tile32(RowAcc<D>& st, float (&va)[kQC], flo
         if (mk == 0xffffu) add_to_class<D>(st, static_cast<int>(c), tb * sb);
         else gather_mixed<D>(st, vb, cls_lane, kQC, 0xffffu, c, mk, tb, sb);
     }
+    return;
 }
 
 // kWide: the frame-level bound that makes the prior recurrence safe everywhere (PriorConst::chain_always) fails for
@@ -804,6 +902,11 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
         const int sub = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+        // values the tile loop needs every iteration, pinned to registers: ptxas otherwise recomputes them from %tid / the shared
+        // window base each time (~25 of a tile's ~200 bookkeeping instructions in the round-2 profile)
+        const uint32_t bar_full = pin_reg(pp.acc_full), bar_empty = pin_reg(pp.acc_empty);
+        const uint32_t tbase = pin_reg(pp.tmem_base + lane_base + static_cast<uint32_t>(sub * 32));
+        const uint32_t lane_is0 = pin_reg(lane == 0 ? 1u : 0u);
         const int W = prm.w_lowres;
         const float w_f = static_cast<float>(W);
         const float h_f = static_cast<float>((prm.n_pixels + W - 1) / W);
@@ -848,6 +951,7 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
             const uint8_t* cls_p = prm.cls + static_cast<size_t>(prm.ref_slot[r]) * prm.p_pad + jp * kTile + sub * 32 + lane;
             PriorConst pc = prior_const(prm.ref_coef[r], inv_w, w_f, h_f);
             uint32_t cls_next = __ldg(cls_p);                        // class byte of logit column `lane`, one tile ahead
+            const bool row_real = m < prm.n_pixels;
             for (int nt = n0; nt < n1; ++nt) {
                 const uint32_t cls_lane = cls_next;
                 {   // prefetch the next tile's class bytes: the load's latency hides behind this tile's arithmetic
@@ -860,28 +964,34 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                             nxt = cls_p + ((jn >= dec.tpf ? jn - dec.tpf : jn) - jp) * kTile;
                         }
                     }
-                    if (!(VOS_ABL & 128) && nt + 1 < n1) cls_next = __ldg(nxt);
+                    if (nt + 1 < n1) cls_next = __ldg(nxt);
                 }
                 const uint32_t valid32 = (jp == dec.tpf - 1) ? ragged : full;
-                mbar_wait_s(pp.acc_full + 8 * buf, aphase);
+                mbar_wait_hint_s(bar_full + 8 * buf, aphase, 20000u);
                 tc_fence_after_sync();
-                const uint32_t taddr = pp.tmem_base + lane_base + buf * kTile + sub * 32;
+                const uint32_t taddr = tbase + buf * kTile;
                 const uint32_t cls0 = __shfl_sync(full, cls_lane, 0);
                 const uint32_t same32 = __ballot_sync(full, cls_lane == cls0);
                 if (valid32 == full && (kWide || pc.chain_always) && !VOS_DBG_ANY(prm)) {
                     float va[kQC], vb[kQC];
-                    if (VOS_ABL & 64) {
-#pragma unroll
-                        for (int i = 0; i < kQC; ++i) { va[i] = static_cast<float>(nt + i) * inv_w; vb[i] = static_cast<float>(nt - i) * inv_w; }
+                    if constexpr (kWide) {
+                        tmem_ld_32x32b_x16(taddr, va);
+                        tmem_ld_32x32b_x16(taddr + kQC, vb);
+                        tmem_ld_wait();
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane_is0) mbar_arrive_s(bar_empty + 8 * buf);
+                        fast_tile32_wide<D>(st, va, vb, cls_lane, cls0, same32, dn, static_cast<float>(x_sub - xm), W - x_sub, pc, inv_w, scale2, w_f);
                     } else {
                         tmem_ld_32x32b_x16(taddr, va);
                         tmem_ld_32x32b_x16(taddr + kQC, vb);
+                        tmem_ld_wait();
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane_is0) mbar_arrive_s(bar_empty + 8 * buf);
+                        if (tile_exps32<D, kSkip>(st, va, vb, scale2, probe, rm_row, row_real))
+                            tile_prior32<D>(st, va, vb, cls_lane, cls0, same32, dn, static_cast<float>(x_sub - xm), W - x_sub, pc, inv_w, w_f);
                     }
-                    tmem_ld_wait();
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_s(pp.acc_empty + 8 * buf);
-                    fast_tile32<D, kWide, kSkip>(st, va, vb, cls_lane, cls0, same32, dn, static_cast<float>(x_sub - xm), W - x_sub, pc, inv_w, scale2, w_f, probe, rm_row, m < prm.n_pixels);
                 } else {
                 int xq = x_sub;
 #pragma unroll 1
@@ -897,7 +1007,7 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                     if (q == 1) {                                    // both halves of this warp's columns are in registers
                         tc_fence_before_sync();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_s(pp.acc_empty + 8 * buf);   // one arrival per warp: 512 per-thread
+                        if (lane_is0) mbar_arrive_s(bar_empty + 8 * buf);       // one arrival per warp: 512 per-thread
                     }                                                            // arrivals serialise on the barrier word
                     const int lane_shift = q * kQC;
                     const uint32_t valid = (valid32 >> lane_shift) & 0xffffu;

@@ -2,40 +2,33 @@
 // predict.py:55 is restricted, per target pixel, to the k reference pixels with the largest logit
 // (ties -> lowest reference index first); prior and label gather are unchanged.  Oracle: oracle.predict(topk=k).
 //
-//   vos_affinity_topk : same TMA -> tcgen05 -> TMEM pipeline as vos_affinity_idx, but the epilogue keeps a
-//                       streaming top-k of (logit * temperature, reference index) per target pixel in shared
-//                       memory -- the (N x P) affinity never reaches HBM.  One epilogue thread owns one target
-//                       pixel and all 128 columns of a tile; candidates above the thread's running k-th value are
-//                       appended to its column of a [slot][128] buffer; when a buffer fills, the warp prunes all of
-//                       its 32 buffers to k entries (bisection on order-preserving integer keys + stable compaction).
-//                       Output: per (CTA, segment) and target pixel the k best (key, index) pairs, index-ascending.
-//   vos_topk_finish   : one warp per target pixel: merges the per-segment lists, selects the global top-k, orders
-//                       it (value descending, index ascending), soft-maxes over the k logits, applies the prior
-//                       in closed form, gathers the label records of the k reference pixels (64-byte coalesced
-//                       loads) and writes prediction / arg-max / new labels / top-k indices.
-//   vos_upsample_mask : stride-8 class map -> full-resolution uint8 mask (ATen legacy 'nearest').
+// Two passes over the tensor cores (the (N x P) affinity never reaches HBM in either), because what made the one-pass
+// streaming selection of round 1 slow was not the selection but the start: until a row has seen its k best logits
+// nearly every logit is a candidate, and every candidate costs a divergent push.  A scan of the affinity without
+// arithmetic is cheap (1 300 cycles per 128 x 128 tile against 2 700 for the full softmax), so:
+//
+//   vos_topk_scan<pass 1>  : TMA -> tcgen05 -> TMEM pipeline of vos_affinity_idx; the epilogue (16 warps, one thread = one
+//                            target pixel x 32 columns per tile) only takes the maximum of its 32 logits:
+//                            bound[(tile * 4 + column group) * 128 + row].  17 instructions per thread and tile.
+//   vos_topk_threshold     : per target pixel the k-th largest of its block maxima, tau.  At least k logits of the row are
+//                            >= tau (k different blocks hold one), so tau is a LOWER bound of the row's k-th largest logit:
+//                            every top-k member is >= tau.  Measured on the synthetic 480p clips (57 780 logits per row):
+//                            5.5 / 36 / 147 logits >= tau for k = 5 / 20 / 50.
+//   vos_topk_scan<pass 2>  : the same contraction again (bit-identical logits: same tiles, same MMA order); a logit is
+//                            looked at only if it is >= tau (a maximum tree and one vote per 16 columns otherwise) and then
+//                            appended to its thread's list in global memory.  A list that fills up is pruned to its k best
+//                            (key descending, index ascending) and the thread's own threshold rises.
+//   vos_topk_finish        : one warp per target pixel: merges the lists (4 column groups x the CTAs of the row), selects
+//                            and orders the global top-k, soft-maxes over the k logits, applies the prior in closed form,
+//                            gathers the label records (64-byte loads), writes prediction / arg-max / new labels / indices.
+//   vos_upsample_mask      : stride-8 class map -> full-resolution uint8 mask (ATen legacy 'nearest').
+// Selection compares fl(logit * temperature) exactly as torch computes it (predict.py:52); ties at the k-th value go to
+// the lowest reference indices (each list keeps its first k ties in index order: it scans indices in ascending order).
 #pragma once
 #include "affinity_idx.cuh"
 #include "topk_params.h"
 
 namespace vosk {
-
-
-// Shape of the top-k epilogue: kSub column groups per tile, 4 * kSub warps, one thread = one target pixel x 128 / kSub
-// columns with its own buffer.  kSub = 1: 112 slots (any k <= 64), one warp per scheduler -- latency bound
-// (profiles/README.md).  More warps hide that latency but shared memory caps the slots per thread (a buffer needs
-// k + 16 slots plus slack between prunes): kSub = 2: 64 slots (k <= 24), kSub = 4: 36 slots (k <= 8) -- at the price
-// of kSub lists per (CTA, segment, pixel) for the finish kernel to merge.
-template <int kSub>
-struct TopkCfg {
-    static constexpr int kEpiWarps = 4 * kSub;
-    static constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp 0 TMA, warp 1 MMA, then the epilogue warps
-    static constexpr int kBuf = kSub == 1 ? 112 : (kSub == 2 ? 64 : 36);   // candidate slots per thread
-    static constexpr int kStages = kSub == 1 ? 3 : 2;         // x 32 KiB of reference chunks in flight
-    static constexpr uint32_t kStride = 512u * kSub;          // bytes between consecutive slots of one thread
-    static constexpr int kCols = kTile / kSub;                // logit columns per thread and tile
-    static constexpr int kSmem = kStages * kTopkGroup * kChunkBytes + 512 + 1024 + kBuf * kTile * kSub * 8;
-};
 
 // order-preserving map float -> uint32 (larger float <=> larger key); -0.0 must be normalised to +0.0 by the caller
 __device__ __forceinline__ uint32_t f2key(float f) {
@@ -45,24 +38,35 @@ __device__ __forceinline__ uint32_t f2key(float f) {
 __device__ __forceinline__ float key2f(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
 }
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+
+// Smallest raw logit x with  fl(x * T) + 0 >= tau  (T >= 0; fl(x * T) is monotone in x): the scan compares raw logits
+// against it instead of multiplying every logit by the temperature.
+__device__ __forceinline__ float raw_threshold(float tau, float T) {
+    if (T == 0.f) return tau <= 0.f ? -INFINITY : INFINITY;         // every product is +0
+    if (!(fabsf(tau) < INFINITY)) return tau;                        // -inf: everything passes; +inf: nothing
+    float x = __fdiv_rn(tau, T);
+    for (int i = 0; i < 4 && !(x * T + 0.f >= tau); ++i) x = nextafterf(x, INFINITY);
+    for (int i = 0; i < 4; ++i) {
+        const float y = nextafterf(x, -INFINITY);
+        if (!(y * T + 0.f >= tau)) break;
+        x = y;
+    }
+    return x;
 }
 
-// Warp-synchronous prune of the 32 candidate buffers of a warp to their k best entries.
-// Buffer of a thread: slots e = 0..cnt-1 at kbase + kStride*e (keys) / ibase + kStride*e (indices), index-ascending.
-// Order: key descending, then index ascending (= slot order among equal keys).  tau <- the k-th best key.
-// On entry tau is a lower bound of every key in the buffer (the k-th best of the last prune, or the key of -inf) and
-// kmax the largest key ever pushed, so no pass is needed to find the search interval; pivots alternate between
-// interpolation on the counts and plain bisection, and the bounds snap to actual keys after every pass (typically 4-6
-// passes over the buffer instead of ~14 with min/max + pure bisection + a separate count).
-template <uint32_t kStride>
-__device__ __forceinline__ void topk_prune(uint32_t kbase, uint32_t ibase, int& cnt, int k, uint32_t& tau, uint32_t kmax) {
+// A thread's candidate list lives in global memory, interleaved with the lists of its warp: slot e of lane l at
+// (list_group * kTopkCap + e) * 32 + l  with list_group = record / 32 -- slot-uniform accesses of a warp coalesce.
+__device__ __forceinline__ size_t topk_slot(size_t rec, int e) {
+    return ((rec >> 5) * kTopkCap + static_cast<size_t>(e)) * 32 + (rec & 31);
+}
+
+// Warp-synchronous prune of the 32 lists of a warp to their k best entries (lists with more than k entries only).
+// Order: key descending, then index ascending (= slot order among equal keys: a thread scans indices in ascending order).
+// tau <- the k-th best key.  On entry tau is a lower bound of every key in the list and kmax the largest key ever pushed,
+// so no pass is needed to find the search interval; pivots alternate between interpolation on the counts and plain
+// bisection, and the bounds snap to actual keys after every pass (typically 4-6 passes).
+__device__ __forceinline__ void topk_prune(uint32_t* __restrict__ keys, int32_t* __restrict__ idxs, int& cnt, int k,
+                                           uint32_t& tau, uint32_t kmax) {
     const uint32_t full = 0xffffffffu;
     const int cmax = __reduce_max_sync(full, cnt);
     const bool active = cnt > k;
@@ -82,7 +86,7 @@ __device__ __forceinline__ void topk_prune(uint32_t kbase, uint32_t ibase, int& 
         uint32_t mn = 0xffffffffu, mxb = 0u;                 // smallest key >= mid, largest key < mid
         for (int e = 0; e < cmax; ++e) {
             if (e < cnt) {
-                const uint32_t key = lds_u32(kbase + kStride * e);
+                const uint32_t key = keys[e * 32];
                 if (key >= mid) { ++c; mn = min(mn, key); }
                 else mxb = max(mxb, key);
             }
@@ -96,13 +100,13 @@ __device__ __forceinline__ void topk_prune(uint32_t kbase, uint32_t ibase, int& 
     int need = k - cgt, w = 0;                               // ties at the k-th key: the first `need` in slot order
     for (int e = 0; e < cmax; ++e) {
         if (active && e < cnt) {
-            const uint32_t key = lds_u32(kbase + kStride * e);
-            const uint32_t idx = lds_u32(ibase + kStride * e);
+            const uint32_t key = keys[e * 32];
+            const int32_t idx = idxs[e * 32];
             bool keep = key > lo;
             if (key == lo && need > 0) { keep = true; --need; }
             if (keep) {
-                sts_u32(kbase + kStride * w, key);
-                sts_u32(ibase + kStride * w, idx);
+                keys[w * 32] = key;
+                idxs[w * 32] = idx;
                 ++w;
             }
         }
@@ -110,114 +114,170 @@ __device__ __forceinline__ void topk_prune(uint32_t kbase, uint32_t ibase, int& 
     if (active) { cnt = w; tau = lo; }
 }
 
-template <bool kSplit, int kSub>
-__global__ void __launch_bounds__(TopkCfg<kSub>::kThreads, 1)
-vos_affinity_topk(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
-                  const __grid_constant__ AffinityParams prm) {
+// kPass = 1: block maxima (prm.topk_bound).  kPass = 2: candidate lists (prm.cand_*), thresholds from prm.topk_tau.
+template <bool kSplit, int kPass>
+__global__ void __launch_bounds__(kIdxThreads, 1)
+vos_topk_scan(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant__ CUtensorMap tmap_lo,
+              const __grid_constant__ AffinityParams prm) {
     using Cfg = IdxCfg<kSplit>;
-    using TC = TopkCfg<kSub>;
-    constexpr int kTopkStages = TC::kStages;
-    constexpr uint32_t kStride = TC::kStride;
     extern __shared__ uint8_t smem_raw[];
-    const IdxPipe pp = idx_setup<kTopkGroup, kTopkStages>(smem_raw, &tmap_hi, &tmap_lo, Cfg::kAccBufs, TC::kEpiWarps);
+    pdl_launch_dependents();
+    const IdxPipe pp = idx_setup<Cfg::kGroup, Cfg::kStages>(smem_raw, &tmap_hi, &tmap_lo, Cfg::kAccBufs, kIdxEpiWarps);
+    pdl_wait();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const vosd::Decomp dec = vosd::make_decomp(prm.n_pixels, prm.n_refs, prm.num_sms);
 
     if (warp == 0) {
-        idx_role_producer<kSplit, kTopkGroup, kTopkStages>(pp, &tmap_hi, &tmap_lo, prm, dec);
+        idx_role_producer<kSplit, Cfg::kGroup, Cfg::kStages>(pp, &tmap_hi, &tmap_lo, prm, dec);
     } else if (warp == 1) {
-        idx_role_mma<kSplit, kTopkGroup, kTopkStages>(pp, prm, dec);
+        idx_role_mma<kSplit, Cfg::kGroup, Cfg::kStages>(pp, prm, dec);
     } else {
         // ================= epilogue: warp w owns TMEM lanes [32*(w%4), +32) = 32 target pixels and the logit columns
-        // [kCols*sub, +kCols) of every tile
+        // [32*sub, +32) of every tile
         const uint32_t full = 0xffffffffu;
         const int quarter = warp & 3;
         const int sub = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-        const uint32_t buf_base = (pp.acc_empty + 8 * kIdxMaxAccBufs + 16 + 127) & ~127u;
-        const uint32_t kbase = buf_base + 4u * (sub * kTile + row);                                  // keys    [kBuf][128 * kSub]
-        const uint32_t ibase = buf_base + TC::kBuf * kTile * kSub * 4 + 4u * (sub * kTile + row);    // indices [kBuf][128 * kSub]
+        const uint32_t bar_full = pin_reg(pp.acc_full), bar_empty = pin_reg(pp.acc_empty);
+        const uint32_t tbase = pin_reg(pp.tmem_base + lane_base + static_cast<uint32_t>(sub * 32));
+        const uint32_t lane_is0 = pin_reg(lane == 0 ? 1u : 0u);
         const int k = prm.topk;
         const float temperature = prm.temperature;
+        const int last_valid = prm.n_pixels - (dec.tpf - 1) * kTile - sub * 32;   // real columns of this warp in a frame's last tile
         vosd::SegIter it(dec, blockIdx.x);
         int m_tile, n0, n1;
         uint32_t buf = 0, aphase = 0;
-        long long n_steps = 0, n_slow = 0, n_push = 0, n_prune = 0;     // profiling counters (vosprop_debug_clocks)
         while (it.next(m_tile, n0, n1)) {
-            idx_stage_target<kSplit>(pp, prm, it.seg, m_tile, row, lane_base, sub, kSub);
+            idx_stage_target<kSplit>(pp, prm, it.seg, m_tile, row, lane_base, sub, kIdxSub);
+            const size_t rec = (static_cast<size_t>(blockIdx.x * dec.max_segs + it.seg) * kIdxSub + sub) * kTile + row;
+            // ---- pass 2 state: this thread's list and thresholds
+            uint32_t* lkeys = nullptr;
+            int32_t* lidx = nullptr;
             int cnt = 0;
-            uint32_t tau = f2key(-INFINITY);       // key of the running k-th best (a lower bound of every buffered key)
-            uint32_t kmax = 0u;                    // largest key pushed in this segment
-            float tau_f = -INFINITY;
+            uint32_t tau_key = 0u, kmax = 0u;
+            float tcmp = INFINITY;             // raw logits >= tcmp are candidates
+            if constexpr (kPass == 2) {
+                lkeys = prm.cand_key + topk_slot(rec, 0);
+                lidx = prm.cand_idx + topk_slot(rec, 0);
+                const int pix = m_tile * kTile + row;
+                const float tau = pix < prm.n_pixels ? prm.topk_tau[pix] : INFINITY;     // rows beyond the frame collect nothing
+                tau_key = f2key(tau + 0.f);
+                tcmp = raw_threshold(tau, temperature);
+            }
+            float* bound = nullptr;
+            if constexpr (kPass == 1)
+                bound = prm.topk_bound + ((static_cast<size_t>(m_tile) * dec.nt + n0) * kIdxSub + sub) * kTile + row;
             int r = n0 / dec.tpf;
             int j = n0 - r * dec.tpf;
             for (int nt = n0; nt < n1; ++nt) {
-                const int n_tile = r * prm.n_pixels + j * kTile + sub * TC::kCols;   // reference index (r*P + pixel) of this thread's column 0
-                const int cols = min(kTile, prm.n_pixels - j * kTile) - sub * TC::kCols;  // its real columns in this tile
-                mbar_wait_s(pp.acc_full + 8 * buf, aphase);
+                mbar_wait_s(bar_full + 8 * buf, aphase);
                 tc_fence_after_sync();
-                const uint32_t taddr = pp.tmem_base + lane_base + buf * kTile + sub * TC::kCols;
-#pragma unroll 1
-                for (int s = 0; s < TC::kCols / kQC; ++s) {
-                    float v[kQC];
-                    tmem_ld_32x32b_x16(taddr + s * kQC, v);
-                    tmem_ld_wait();
-                    if (s == TC::kCols / kQC - 1) {                           // this thread's columns of the tile are consumed
-                        tc_fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_s(pp.acc_empty + 8 * buf);  // one arrival per warp
-                    }
-                    const int nv = cols - s * kQC;
-                    if (nv <= 0) continue;
-                    ++n_steps;
+                const uint32_t taddr = tbase + buf * kTile;
+                float va[kQC], vb[kQC];
+                tmem_ld_32x32b_x16(taddr, va);
+                tmem_ld_32x32b_x16(taddr + kQC, vb);
+                tmem_ld_wait();
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane_is0) mbar_arrive_s(bar_empty + 8 * buf);
+                if (j == dec.tpf - 1 && last_valid < 32) {                     // ragged last tile of a frame: pad columns never win
 #pragma unroll
                     for (int i = 0; i < kQC; ++i) {
-                        v[i] = v[i] * temperature + 0.0f;                     // predict.py:52 (fp32 product); -0 -> +0
-                        if (i >= nv) v[i] = -INFINITY;
+                        if (i >= last_valid) va[i] = -INFINITY;
+                        if (i + kQC >= last_valid) vb[i] = -INFINITY;
                     }
-                    if (!__any_sync(full, max16(v) > tau_f)) continue;        // nothing beats any lane's k-th best
-                    ++n_slow;
+                }
+                const float ma = max16(va), mb = max16(vb);
+                if constexpr (kPass == 1) {
+                    *bound = fmaxf(ma, mb) * temperature + 0.0f;            // predict.py:52 (fp32 product); -0 -> +0
+                    bound += kIdxSub * kTile;
+                } else {
+                    const int n_tile = r * prm.n_pixels + j * kTile + sub * 32;   // reference index (r*P + pixel) of this thread's column 0
 #pragma unroll
-                    for (int i = 0; i < kQC; ++i) {
-                        if (v[i] > tau_f) {
-                            const uint32_t key = f2key(v[i]);
-                            kmax = max(kmax, key);
-                            ++n_push;
-                            sts_u32(kbase + kStride * cnt, key);
-                            sts_u32(ibase + kStride * cnt, static_cast<uint32_t>(n_tile + s * kQC + i));
-                            ++cnt;
+                    for (int h = 0; h < 2; ++h) {
+                        const float (&v)[kQC] = h ? vb : va;
+                        if (!__any_sync(full, (h ? mb : ma) >= tcmp)) continue;     // nothing reaches any lane's threshold
+#pragma unroll
+                        for (int i = 0; i < kQC; ++i) {
+                            const bool hit = v[i] >= tcmp;
+                            if (__any_sync(full, hit)) {                            // warp-uniform: columns without a hit cost a vote
+                                if (hit) {
+                                    const uint32_t key = f2key(v[i] * temperature + 0.0f);
+                                    kmax = max(kmax, key);
+                                    lkeys[cnt * 32] = key;
+                                    lidx[cnt * 32] = n_tile + h * kQC + i;
+                                    ++cnt;
+                                }
+                            }
                         }
-                    }
-                    if (__any_sync(full, cnt > TC::kBuf - kQC)) {
-                        ++n_prune;
-                        topk_prune<kStride>(kbase, ibase, cnt, k, tau, kmax);
-                        tau_f = key2f(tau);
+                        if (__any_sync(full, cnt > kTopkCap - kQC)) {
+                            const int before = cnt;
+                            topk_prune(lkeys, lidx, cnt, k, tau_key, kmax);
+                            // after a prune the list holds k entries >= tau, all with lower indices than anything still to
+                            // come: a later tie at tau cannot enter any more -> strictly greater from now on
+                            if (cnt < before) tcmp = raw_threshold(nextafterf(key2f(tau_key), INFINITY), temperature);
+                        }
                     }
                 }
                 if (++buf == Cfg::kAccBufs) { buf = 0; aphase ^= 1; }
                 if (++j == dec.tpf) { j = 0; ++r; }
             }
-            topk_prune<kStride>(kbase, ibase, cnt, k, tau, kmax);
-            // ---- this thread's list of the target pixel for this segment: cnt <= k entries, index-ascending
-            const size_t rec = (static_cast<size_t>(blockIdx.x * dec.max_segs + it.seg) * kSub + sub) * kTile + row;
-            prm.cand_cnt[rec] = cnt;
-            uint32_t* ck = prm.cand_key + rec * kTopkMax;
-            int32_t* ci = prm.cand_idx + rec * kTopkMax;
-            for (int e = 0; e < cnt; ++e) {
-                ck[e] = lds_u32(kbase + kStride * e);
-                ci[e] = static_cast<int32_t>(lds_u32(ibase + kStride * e));
+            if constexpr (kPass == 2) {
+                if (__any_sync(full, cnt > k)) topk_prune(lkeys, lidx, cnt, k, tau_key, kmax);
+                prm.cand_cnt[rec] = cnt;          // this thread's list of the target pixel for this segment: index-ascending
             }
-        }
-        if (prm.dbg_clk && warp == 2 && lane == 0) {
-            prm.dbg_clk[blockIdx.x * 16 + 9] = n_steps;
-            prm.dbg_clk[blockIdx.x * 16 + 10] = n_slow;
-            prm.dbg_clk[blockIdx.x * 16 + 11] = n_push;
-            prm.dbg_clk[blockIdx.x * 16 + 12] = n_prune;
         }
     }
     idx_teardown(pp);
+}
+
+// Per target pixel the k-th largest of its block maxima (pass 1) -> tau (a lower bound of the row's k-th largest
+// fl(logit * temperature)); -inf when the row has fewer than k blocks.  One CTA per `rows` consecutive pixels of one
+// target tile: the maxima are brought into shared memory transposed (rows x blocks; the global layout is blocks x 128 rows),
+// then one warp per row bisects on the order-preserving keys with the bounds snapping to actual keys.
+__global__ void __launch_bounds__(256) vos_topk_threshold(const float* __restrict__ bound, float* __restrict__ tau,
+                                                          int n_pixels, int n_blocks, int k, int rows) {
+    extern __shared__ uint32_t tkeys[];                    // [rows][stride]
+    const uint32_t full = 0xffffffffu;
+    const int stride = n_blocks | 1;                       // odd: the transposing stores spread over the banks
+    const int pix0 = blockIdx.x * rows;
+    const int mt = pix0 / kTile, row0 = pix0 % kTile;
+    const float* src = bound + static_cast<size_t>(mt) * n_blocks * kTile + row0;
+    for (int i = threadIdx.x; i < n_blocks * rows; i += blockDim.x) {
+        const int b = i / rows, rr = i - b * rows;
+        tkeys[rr * stride + b] = f2key(src[static_cast<size_t>(b) * kTile + rr] + 0.0f);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int rr = warp; rr < rows; rr += blockDim.x >> 5) {
+        const int pix = pix0 + rr;
+        if (pix >= n_pixels) continue;
+        const uint32_t* keys = tkeys + rr * stride;
+        float result = -INFINITY;
+        if (n_blocks >= k) {
+            uint32_t lo = 0xffffffffu, hi = 0u;
+            for (int e = lane; e < n_blocks; e += 32) { lo = min(lo, keys[e]); hi = max(hi, keys[e]); }
+            lo = __reduce_min_sync(full, lo);
+            hi = __reduce_max_sync(full, hi);
+            while (lo < hi) {                               // invariant: #{key >= lo} >= k, #{key > hi} < k
+                const uint32_t mid = lo + ((hi - lo) >> 1) + 1u;
+                int c = 0;
+                uint32_t mn = 0xffffffffu, mxb = 0u;
+                for (int e = lane; e < n_blocks; e += 32) {
+                    const uint32_t key = keys[e];
+                    if (key >= mid) { ++c; mn = min(mn, key); }
+                    else mxb = max(mxb, key);
+                }
+                c = __reduce_add_sync(full, c);
+                if (c >= k) lo = __reduce_min_sync(full, mn);
+                else hi = __reduce_max_sync(full, mxb);
+            }
+            result = key2f(lo);
+        }
+        if (lane == 0) tau[pix] = result;
+    }
 }
 
 // -------------------------------------------------------------------------------------------
@@ -249,8 +309,8 @@ __global__ void __launch_bounds__(kFinishWarps * 32) vos_topk_finish(const TopkF
             const size_t rec = (static_cast<size_t>(c * dec.max_segs + seg) * prm.n_sub + sub) * kTile + row;
             const int n = fp.cand_cnt[rec];
             for (int e = lane; e < n; e += 32) {
-                keys[C + e] = fp.cand_key[rec * kTopkMax + e];
-                idxs[C + e] = static_cast<uint32_t>(fp.cand_idx[rec * kTopkMax + e]);
+                keys[C + e] = fp.cand_key[topk_slot(rec, e)];
+                idxs[C + e] = static_cast<uint32_t>(fp.cand_idx[topk_slot(rec, e)]);
             }
             C += n;
         }

@@ -97,6 +97,26 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
         if (++polls > (1u << 26)) __trap();
     }
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes or `hint_ns` pass, instead of
+// coming back after the default time slice (16 epilogue warps polling cost 8 % of the fused kernel's issue slots, round 2)
+__device__ __forceinline__ bool mbar_try_wait_hint_s(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_hint_s(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+    if (mbar_try_wait_s(bar, parity)) return;
+    uint32_t polls = 0;
+    while (!mbar_try_wait_hint_s(bar, parity, hint_ns)) {
+        if (++polls > (1u << 24)) __trap();
+    }
+}
 __device__ __forceinline__ void mbar_wait_relaxed_s(uint32_t bar, uint32_t parity, uint32_t ns) {
     if (mbar_try_wait_s(bar, parity)) return;
     uint32_t polls = 0;
@@ -232,6 +252,12 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                  ::"r"(smem_u32(bar)) : "memory");
+}
+
+// an opaque copy: the compiler must keep the value in a register instead of recomputing it where it is used
+__device__ __forceinline__ uint32_t pin_reg(uint32_t x) {
+    asm volatile("" : "+r"(x));
+    return x;
 }
 
 // ---------------------------------------------------------------- programmatic dependent launch
