@@ -91,8 +91,9 @@ __device__ __forceinline__ void idx_role_producer(const IdxPipe& pp, const CUten
     int m_tile, n0, n1;
     uint32_t stage = 0, phase = 0;
     long long t_wait = 0, t_begin = VOS_CLK();
+    const int tstep = prm.tile_step > 1 ? prm.tile_step : 1;                     // top-k pass 1: every tstep-th tile of a row
     while (it.next(m_tile, n0, n1)) {
-        for (int nt = n0; nt < n1; ++nt) {
+        for (int nt = n0 + (tstep - n0 % tstep) % tstep; nt < n1; nt += tstep) {
             const int r = nt / dec.tpf;
             int jt = nt - r * dec.tpf;
             if (prm.tile_stride > 1) jt = (jt * prm.tile_stride) % dec.tpf;      // work-balancing tile order (block skipping)
@@ -149,12 +150,13 @@ __device__ __forceinline__ void idx_role_mma(const IdxPipe& pp, const AffinityPa
     unsigned long long ns_begin;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_begin));
 #endif
+    const int tstep = prm.tile_step > 1 ? prm.tile_step : 1;
     while (it.next(m_tile, n0, n1)) {
         long long t0 = VOS_CLK();
         mbar_wait_s(pp.q_full, it.seg & 1);
         t_q += VOS_CLK() - t0;
         tc_fence_after_sync();
-        for (int nt = n0; nt < n1; ++nt) {
+        for (int nt = n0 + (tstep - n0 % tstep) % tstep; nt < n1; nt += tstep) {
             t0 = VOS_CLK();
             mbar_wait_relaxed_s(pp.acc_empty + 8 * buf, aphase ^ 1, 32);
             t_acc += VOS_CLK() - t0;

@@ -42,8 +42,10 @@ __device__ __forceinline__ float key2f(uint32_t k) {
 // Smallest raw logit x with  fl(x * T) + 0 >= tau  (T >= 0; fl(x * T) is monotone in x): the scan compares raw logits
 // against it instead of multiplying every logit by the temperature.
 __device__ __forceinline__ float raw_threshold(float tau, float T) {
-    if (T == 0.f) return tau <= 0.f ? -INFINITY : INFINITY;         // every product is +0
-    if (!(fabsf(tau) < INFINITY)) return tau;                        // -inf: everything passes; +inf: nothing
+    // "everything passes" is the lowest FINITE float: the -inf that masks the pad columns of a ragged tile must fail the test
+    if (T == 0.f) return tau <= 0.f ? -3.402823466e38f : INFINITY;  // every product is +0
+    if (tau == -INFINITY) return -3.402823466e38f;
+    if (!(tau < INFINITY)) return INFINITY;                          // +inf (rows beyond the frame) or NaN: nothing passes
     float x = __fdiv_rn(tau, T);
     for (int i = 0; i < 4 && !(x * T + 0.f >= tau); ++i) x = nextafterf(x, INFINITY);
     for (int i = 0; i < 4; ++i) {
@@ -167,11 +169,13 @@ vos_topk_scan(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant
                 tcmp = raw_threshold(tau, temperature);
             }
             float* bound = nullptr;
+            const int tstep = kPass == 1 ? prm.tile_step : 1;            // pass 1 may visit every tstep-th reference tile only
+            const int nt_first = n0 + (tstep - n0 % tstep) % tstep;
             if constexpr (kPass == 1)
-                bound = prm.topk_bound + ((static_cast<size_t>(m_tile) * dec.nt + n0) * kIdxSub + sub) * kTile + row;
-            int r = n0 / dec.tpf;
-            int j = n0 - r * dec.tpf;
-            for (int nt = n0; nt < n1; ++nt) {
+                bound = prm.topk_bound + ((static_cast<size_t>(m_tile) * dec.nt + nt_first) * kIdxSub + sub) * kTile + row;
+            int r = nt_first / dec.tpf;
+            int j = nt_first - r * dec.tpf;
+            for (int nt = nt_first; nt < n1; nt += tstep) {
                 mbar_wait_s(bar_full + 8 * buf, aphase);
                 tc_fence_after_sync();
                 const uint32_t taddr = tbase + buf * kTile;
@@ -192,7 +196,7 @@ vos_topk_scan(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant
                 const float ma = max16(va), mb = max16(vb);
                 if constexpr (kPass == 1) {
                     *bound = fmaxf(ma, mb) * temperature + 0.0f;            // predict.py:52 (fp32 product); -0 -> +0
-                    bound += kIdxSub * kTile;
+                    bound += tstep * kIdxSub * kTile;
                 } else {
                     const int n_tile = r * prm.n_pixels + j * kTile + sub * 32;   // reference index (r*P + pixel) of this thread's column 0
 #pragma unroll
@@ -222,7 +226,8 @@ vos_topk_scan(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant
                     }
                 }
                 if (++buf == Cfg::kAccBufs) { buf = 0; aphase ^= 1; }
-                if (++j == dec.tpf) { j = 0; ++r; }
+                j += tstep;
+                while (j >= dec.tpf) { j -= dec.tpf; ++r; }
             }
             if constexpr (kPass == 2) {
                 if (__any_sync(full, cnt > k)) topk_prune(lkeys, lidx, cnt, k, tau_key, kmax);
@@ -235,46 +240,79 @@ vos_topk_scan(const __grid_constant__ CUtensorMap tmap_hi, const __grid_constant
 
 // Per target pixel the k-th largest of its block maxima (pass 1) -> tau (a lower bound of the row's k-th largest
 // fl(logit * temperature)); -inf when the row has fewer than k blocks.  One CTA per `rows` consecutive pixels of one
-// target tile: the maxima are brought into shared memory transposed (rows x blocks; the global layout is blocks x 128 rows),
-// then one warp per row bisects on the order-preserving keys with the bounds snapping to actual keys.
-__global__ void __launch_bounds__(256) vos_topk_threshold(const float* __restrict__ bound, float* __restrict__ tau,
-                                                          int n_pixels, int n_blocks, int k, int rows) {
-    extern __shared__ uint32_t tkeys[];                    // [rows][stride]
+// target tile: the maxima are brought into shared memory transposed (rows x blocks; the global layout is blocks x 128 rows,
+// so `rows` = 8 pixels read whole 32-byte sectors), then one warp per row runs a radix select on the order-preserving
+// keys: four passes of 8 bits, each a 256-bin histogram of the keys that still match the prefix (shared-memory atomics)
+// and a suffix scan over the bins (8 per lane) for the digit that holds the k-th largest.
+// tile_step: pass 1 visited every tile_step-th reference tile of a row only (blocks of the others are not read).
+constexpr int kThrWarps = 8;
+__global__ void __launch_bounds__(kThrWarps * 32) vos_topk_threshold(const float* __restrict__ bound, float* __restrict__ tau,
+                                                                     int n_pixels, int n_tiles, int tile_step, int k, int rows_log2) {
+    extern __shared__ uint32_t tkeys[];                    // [rows][stride] keys, then [kThrWarps][256] histograms
     const uint32_t full = 0xffffffffu;
+    const int rows = 1 << rows_log2;
+    const int n_vis = (n_tiles + tile_step - 1) / tile_step;          // visited tiles per row
+    const int n_blocks = n_vis * kIdxSub;
     const int stride = n_blocks | 1;                       // odd: the transposing stores spread over the banks
-    const int pix0 = blockIdx.x * rows;
+    uint32_t* hist_all = tkeys + rows * stride;
+    const int pix0 = blockIdx.x << rows_log2;
     const int mt = pix0 / kTile, row0 = pix0 % kTile;
-    const float* src = bound + static_cast<size_t>(mt) * n_blocks * kTile + row0;
-    for (int i = threadIdx.x; i < n_blocks * rows; i += blockDim.x) {
-        const int b = i / rows, rr = i - b * rows;
-        tkeys[rr * stride + b] = f2key(src[static_cast<size_t>(b) * kTile + rr] + 0.0f);
+    const float* src = bound + static_cast<size_t>(mt) * n_tiles * kIdxSub * kTile + row0;
+    for (int i = threadIdx.x; i < n_blocks << rows_log2; i += blockDim.x) {
+        const int b = i >> rows_log2, rr = i & (rows - 1);
+        const int t = (b >> 2) * tile_step, sub = b & 3;
+        tkeys[rr * stride + b] = f2key(src[static_cast<size_t>(t * kIdxSub + sub) * kTile + rr] + 0.0f);
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int rr = warp; rr < rows; rr += blockDim.x >> 5) {
+    uint32_t* hist = hist_all + warp * 256;
+    for (int rr = warp; rr < rows; rr += kThrWarps) {
         const int pix = pix0 + rr;
-        if (pix >= n_pixels) continue;
+        if (pix >= n_pixels) continue;                     // warp-uniform
         const uint32_t* keys = tkeys + rr * stride;
         float result = -INFINITY;
         if (n_blocks >= k) {
-            uint32_t lo = 0xffffffffu, hi = 0u;
-            for (int e = lane; e < n_blocks; e += 32) { lo = min(lo, keys[e]); hi = max(hi, keys[e]); }
-            lo = __reduce_min_sync(full, lo);
-            hi = __reduce_max_sync(full, hi);
-            while (lo < hi) {                               // invariant: #{key >= lo} >= k, #{key > hi} < k
-                const uint32_t mid = lo + ((hi - lo) >> 1) + 1u;
-                int c = 0;
-                uint32_t mn = 0xffffffffu, mxb = 0u;
+            uint32_t prefix = 0u, mask = 0u;
+            int kk = k;                                    // rank (from the top) of the wanted key among the keys matching the prefix
+#pragma unroll 1
+            for (int shift = 24; shift >= 0; shift -= 8) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) hist[lane * 8 + i] = 0u;
+                __syncwarp();
                 for (int e = lane; e < n_blocks; e += 32) {
                     const uint32_t key = keys[e];
-                    if (key >= mid) { ++c; mn = min(mn, key); }
-                    else mxb = max(mxb, key);
+                    if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
                 }
-                c = __reduce_add_sync(full, c);
-                if (c >= k) lo = __reduce_min_sync(full, mn);
-                else hi = __reduce_max_sync(full, mxb);
+                __syncwarp();
+                uint32_t c[8], mine = 0u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { c[i] = hist[lane * 8 + i]; mine += c[i]; }
+                uint32_t above = mine;                     // inclusive suffix sum over the lanes: bins >= 8 * lane
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const uint32_t o = __shfl_down_sync(full, above, off);
+                    if (lane + off < 32) above += o;
+                }
+                above -= mine;                             // keys in the bins of higher lanes
+                const bool here = above < static_cast<uint32_t>(kk) && static_cast<uint32_t>(kk) <= above + mine;
+                uint32_t digit = 0u, higher = 0u;
+                if (here) {
+                    uint32_t acc = above;
+#pragma unroll
+                    for (int i = 7; i >= 0; --i) {
+                        if (acc < static_cast<uint32_t>(kk) && static_cast<uint32_t>(kk) <= acc + c[i]) { digit = lane * 8 + i; higher = acc; }
+                        acc += c[i];
+                    }
+                }
+                const int src_lane = __ffs(__ballot_sync(full, here)) - 1;
+                digit = __shfl_sync(full, digit, src_lane);
+                higher = __shfl_sync(full, higher, src_lane);
+                prefix |= digit << shift;
+                mask |= 255u << shift;
+                kk -= static_cast<int>(higher);
+                __syncwarp();
             }
-            result = key2f(lo);
+            result = key2f(prefix);
         }
         if (lane == 0) tau[pix] = result;
     }
@@ -301,18 +339,42 @@ __global__ void __launch_bounds__(kFinishWarps * 32) vos_topk_finish(const TopkF
     const int mt = pix / kTile, row = pix % kTile;
     const int64_t lin_lo = static_cast<int64_t>(mt) * dec.nt;
     const int c_first = vosd::cta_of(dec, lin_lo), c_last = vosd::cta_of(dec, lin_lo + dec.nt - 1);
-    // ---- gather the lists of every (CTA, segment, column group) that saw this pixel's row
+    // ---- gather the lists of every (CTA, segment, column group) that saw this pixel's row: lane l owns lists l, l + 32, ...
+    // (all counts are fetched at once, a warp scan places the lists, every lane copies its own -- the loads of different
+    // lists are independent of one another)
+    const int n_lists = (c_last - c_first + 1) * prm.n_sub;
+    constexpr int kListsPerLane = 4;                       // <= 128 lists per pixel (the host keeps lists x k <= kTopkMaxCand)
+    size_t recs[kListsPerLane];
+    int cnts[kListsPerLane], offs[kListsPerLane];
     int C = 0;
-    for (int c = c_first; c <= c_last; ++c) {
-        const int seg = mt - static_cast<int>(vosd::cta_begin(dec, c) / dec.nt);
-        for (int sub = 0; sub < prm.n_sub; ++sub) {
-            const size_t rec = (static_cast<size_t>(c * dec.max_segs + seg) * prm.n_sub + sub) * kTile + row;
-            const int n = fp.cand_cnt[rec];
-            for (int e = lane; e < n; e += 32) {
-                keys[C + e] = fp.cand_key[topk_slot(rec, e)];
-                idxs[C + e] = static_cast<uint32_t>(fp.cand_idx[topk_slot(rec, e)]);
-            }
-            C += n;
+#pragma unroll
+    for (int q = 0; q < kListsPerLane; ++q) {
+        const int li = lane + 32 * q;
+        cnts[q] = 0;
+        recs[q] = 0;
+        if (li < n_lists) {
+            const int c = c_first + li / prm.n_sub, sub = li % prm.n_sub;
+            const int seg = mt - static_cast<int>(vosd::cta_begin(dec, c) / dec.nt);
+            recs[q] = (static_cast<size_t>(c * dec.max_segs + seg) * prm.n_sub + sub) * kTile + row;
+            cnts[q] = fp.cand_cnt[recs[q]];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kListsPerLane; ++q) {
+        int incl = cnts[q];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int o = __shfl_up_sync(full, incl, off);
+            if (lane >= off) incl += o;
+        }
+        offs[q] = C + incl - cnts[q];
+        C += __shfl_sync(full, incl, 31);
+    }
+#pragma unroll
+    for (int q = 0; q < kListsPerLane; ++q) {
+        for (int e = 0; e < cnts[q]; ++e) {
+            keys[offs[q] + e] = fp.cand_key[topk_slot(recs[q], e)];
+            idxs[offs[q] + e] = static_cast<uint32_t>(fp.cand_idx[topk_slot(recs[q], e)]);
         }
     }
     __syncwarp();

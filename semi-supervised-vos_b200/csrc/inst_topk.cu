@@ -1,20 +1,30 @@
-// vos_affinity_topk<split, n_sub>
+// top-k extension: vos_topk_scan<split, pass>, vos_topk_threshold, vos_topk_finish, vos_upsample_mask
 #include "launch.h"
 #include "affinity_topk.cuh"
 
 namespace vosk {
 
-cudaError_t launch_affinity_topk(bool split, int n_sub, int grid, cudaStream_t st, const CUtensorMap& tmap_hi, const CUtensorMap& tmap_lo,
-                                 const AffinityParams& prm) {
+cudaError_t launch_topk_scan(bool split, int pass, int grid, cudaStream_t st, const CUtensorMap& tmap_hi, const CUtensorMap& tmap_lo,
+                             const AffinityParams& prm) {
     void (*kern)(CUtensorMap, CUtensorMap, AffinityParams) =
-        n_sub == 4 ? (split ? vos_affinity_topk<true, 4> : vos_affinity_topk<false, 4>)
-      : n_sub == 2 ? (split ? vos_affinity_topk<true, 2> : vos_affinity_topk<false, 2>)
-                   : (split ? vos_affinity_topk<true, 1> : vos_affinity_topk<false, 1>);
-    const int smem = n_sub == 4 ? TopkCfg<4>::kSmem : (n_sub == 2 ? TopkCfg<2>::kSmem : TopkCfg<1>::kSmem);
-    const int threads = n_sub == 4 ? TopkCfg<4>::kThreads : (n_sub == 2 ? TopkCfg<2>::kThreads : TopkCfg<1>::kThreads);
-    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        pass == 1 ? (split ? vos_topk_scan<true, 1> : vos_topk_scan<false, 1>) : (split ? vos_topk_scan<true, 2> : vos_topk_scan<false, 2>);
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kIdxSmem);
     if (ce != cudaSuccess) return ce;
-    kern<<<grid, threads, smem, st>>>(tmap_hi, tmap_lo, prm);
+    return launch_pdl(kern, grid, kIdxThreads, kIdxSmem, st, tmap_hi, tmap_lo, prm);
+}
+
+// rows per CTA: 8 (whole 32-byte sectors of the block maxima) or fewer when the row of keys is long
+cudaError_t launch_topk_threshold(const float* bound, float* tau, int n_pixels, int n_tiles, int tile_step, int k, cudaStream_t st) {
+    const size_t budget = 200 * 1024, hist = kThrWarps * 256 * 4;
+    const int n_blocks = (n_tiles + tile_step - 1) / tile_step * kIdxSub;
+    int rows_log2 = 3;
+    while (rows_log2 > 0 && (static_cast<size_t>(n_blocks | 1) << rows_log2) * 4 + hist > budget) --rows_log2;
+    const size_t smem = (static_cast<size_t>(n_blocks | 1) << rows_log2) * 4 + hist;
+    if (smem > budget) return cudaErrorInvalidValue;
+    cudaError_t ce = cudaFuncSetAttribute(vos_topk_threshold, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(budget));
+    if (ce != cudaSuccess) return ce;
+    const int rows = 1 << rows_log2;
+    vos_topk_threshold<<<(n_pixels + rows - 1) / rows, kThrWarps * 32, smem, st>>>(bound, tau, n_pixels, n_tiles, tile_step, k, rows_log2);
     return cudaGetLastError();
 }
 

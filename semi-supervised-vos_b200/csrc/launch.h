@@ -32,9 +32,6 @@ cudaError_t launch_affinity_idx(int D, bool split, bool wide, bool skip, int gri
 // vos_affinity_tc<D> (dense label records) / vos_affinity_simt<D> (fp32 checker); D in {2, 3, 4, 6, 8, 11, 14}
 cudaError_t launch_affinity_dense(int D, bool simt, int grid, cudaStream_t st, const CUtensorMap& tmap_hi, const CUtensorMap& tmap_lo,
                                   const AffinityParams& prm);
-// vos_affinity_topk<split, n_sub>
-cudaError_t launch_affinity_topk(bool split, int n_sub, int grid, cudaStream_t st, const CUtensorMap& tmap_hi, const CUtensorMap& tmap_lo,
-                                 const AffinityParams& prm);
 
 // per-D pieces (one translation unit each)
 template <int D> cudaError_t launch_idx_d(bool split, bool wide, bool skip, int grid, cudaStream_t st, const CUtensorMap& tmap_hi,

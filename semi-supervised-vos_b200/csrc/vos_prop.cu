@@ -69,6 +69,9 @@ struct vosprop_engine {
     int32_t* cand_idx = nullptr;
     int32_t* cand_cnt = nullptr;
     uint8_t* low_scratch = nullptr;   // stride-8 class map when the caller wants only the full-resolution mask
+    float* topk_bound = nullptr;      // block maxima of the first scan (grows on demand)
+    size_t topk_bound_floats = 0;
+    float* topk_tau = nullptr;        // [p_pad_cap] per-pixel threshold of the second scan
     // decomposition tables of the merge kernel, one per reference count (cached until the next reset)
     int32_t* tables = nullptr;        // device [VOSPROP_MAX_REFS + 1][table_stride]
     int block_skip = 0;               // vosprop_block_skip: fused kernel with exact skipping of all-zero blocks
@@ -168,49 +171,79 @@ int check_frame(const vosprop_engine* e, int frame_idx) {
 }
 
 
-// Top-k extension (not in the reference): fused affinity + streaming top-k, then per-pixel finish, then up-sample.
+// Top-k extension (not in the reference): two scans of the affinity (block maxima -> per-row threshold -> candidate lists),
+// then the per-pixel finish, then the up-sampling of the mask (affinity_topk.cuh).
 int propagate_topk(vosprop_engine* e, const vosprop_step* s, vosk::AffinityParams ap, const vosd::Decomp& dec_in, cudaStream_t st) {
-    // Lists merged per target pixel = CTAs whose ranges intersect one target tile's row of the tile grid.  Small maps
-    // with many references would spread one row over dozens of CTAs: shrink the grid until a row has <= 16 lists.
+    // Lists merged per target pixel = 4 column groups x the CTAs whose ranges intersect one target tile's row of the tile
+    // grid.  Small maps with many references would spread one row over dozens of CTAs: shrink the grid until the finish
+    // kernel's merge buffer (kTopkMaxCand) holds k entries of every list.
     int grid_cap = e->num_sms;
+    const int64_t max_lists = std::max<int64_t>(1, vosk::kTopkMaxCand / (static_cast<int64_t>(vosk::kIdxSub) * s->topk));
     {
-        const int64_t min_per_cta = (dec_in.nt + 15) / 16;
+        const int64_t min_per_cta = max_lists > 1 ? (dec_in.nt + max_lists - 2) / (max_lists - 1) : dec_in.total;
         if (dec_in.total / grid_cap < min_per_cta) grid_cap = static_cast<int>(std::max<int64_t>(1, dec_in.total / min_per_cta));
     }
     const vosd::Decomp dec = vosd::make_decomp(e->P, s->n_refs, grid_cap);
     const int64_t per_cta = dec.total / dec.grid;
     const int64_t lists = (dec.nt + per_cta - 1) / per_cta + 1;
-    // small k: more epilogue warps with smaller per-thread buffers (n_sub lists per CTA and segment)
-    int n_sub = s->topk <= vosk::kTopkK16 ? 4 : (s->topk <= vosk::kTopkK8 ? 2 : 1);
-    while (n_sub > 1 && lists * n_sub * s->topk > vosk::kTopkMaxCand) n_sub >>= 1;
-    if (lists * n_sub * s->topk > vosk::kTopkMaxCand)
-        return fail(VOSPROP_ERR_UNSUPPORTED, "top-k: %lld lists x k=%d candidates per target pixel (max %d)", (long long)(lists * n_sub),
+    if (lists * vosk::kIdxSub * s->topk > vosk::kTopkMaxCand)
+        return fail(VOSPROP_ERR_UNSUPPORTED, "top-k: %lld lists x k=%d candidates per target pixel (max %d)", (long long)(lists * vosk::kIdxSub),
                     s->topk, vosk::kTopkMaxCand);
+    if (static_cast<size_t>(dec.grid) * dec.max_segs * vosk::kIdxSub > e->partial_records)
+        return fail(VOSPROP_ERR_UNSUPPORTED, "top-k: list table too small (grid %d x segs %d)", dec.grid, dec.max_segs);
     ap.num_sms = grid_cap;
     if (!e->cand_key) {
         const size_t rows = e->partial_records * vosk::kTile;     // partial_records counts 4 column groups per (CTA, segment)
-        cudaError_t a1 = cudaMalloc(&e->cand_key, rows * vosk::kTopkMax * 4);
-        cudaError_t a2 = cudaMalloc(&e->cand_idx, rows * vosk::kTopkMax * 4);
+        cudaError_t a1 = cudaMalloc(&e->cand_key, rows * vosk::kTopkCap * 4);
+        cudaError_t a2 = cudaMalloc(&e->cand_idx, rows * vosk::kTopkCap * 4);
         cudaError_t a3 = cudaMalloc(&e->cand_cnt, rows * 4);
         cudaError_t a4 = cudaMalloc(&e->low_scratch, static_cast<size_t>(e->cfg.max_pixels));
-        if (a1 != cudaSuccess || a2 != cudaSuccess || a3 != cudaSuccess || a4 != cudaSuccess)
+        cudaError_t a5 = cudaMalloc(&e->topk_tau, static_cast<size_t>(e->p_pad_cap) * 4);
+        if (a1 != cudaSuccess || a2 != cudaSuccess || a3 != cudaSuccess || a4 != cudaSuccess || a5 != cudaSuccess)
             return fail(VOSPROP_ERR_CUDA, "cudaMalloc of the top-k candidate lists failed (%zu rows)", rows);
+    }
+    // block maxima of pass 1: 4 x 128 floats per 128 x 128 logit tile (480p, 9 references: 48 MB); grows on demand
+    const size_t bound_floats = static_cast<size_t>(dec.total) * vosk::kIdxSub * vosk::kTile;
+    if (bound_floats > e->topk_bound_floats) {
+        if (e->topk_bound) {
+            VOS_CUDA(cudaStreamSynchronize(st));          // a scan of an earlier step may still be writing the old buffer
+            cudaFree(e->topk_bound);
+            e->topk_bound = nullptr;
+            e->topk_bound_floats = 0;
+        }
+        if (cudaMalloc(&e->topk_bound, bound_floats * 4) != cudaSuccess)
+            return fail(VOSPROP_ERR_CUDA, "cudaMalloc of the top-k block maxima failed (%zu MB)", bound_floats * 4 >> 20);
+        e->topk_bound_floats = bound_floats;
     }
     ap.temperature = s->temperature;
     ap.topk = s->topk;
     ap.cand_key = e->cand_key; ap.cand_idx = e->cand_idx; ap.cand_cnt = e->cand_cnt;
+    ap.topk_bound = e->topk_bound; ap.topk_tau = e->topk_tau;
     {
         TimedLaunch timed(e, VOSPROP_T_AFFINITY, st);
-        VOS_CUDA(vosk::launch_affinity_topk(ap.feat_fmt == vosk::kFmtSplit, n_sub, dec.grid, st, e->tmap_hi, e->tmap_lo, ap));
+        const bool split = ap.feat_fmt == vosk::kFmtSplit;
+        // The first scan visits every tile_step-th reference tile of a row only: any subset of a row's logits gives a valid
+        // lower bound of its k-th largest.  A third of the tiles costs a third of the scan and about triples the candidates
+        // of the second one, which is cheap while the lists stay short (measured at 480p, 9 references, frames/s for
+        // steps 1 / 2 / 3 / 4 / 6:  k = 5: 2583 / 3474 / 3926 / 4067 / 4148;  k = 20: 2550 / 3382 / 3788 / 3764 / 3230;
+        // k = 50: 2468 / 3181 / 3384 / 2591 / 328 -- past the knee the lists overflow and every overflow is a prune).
+        int tile_step = s->topk <= 8 ? 4 : (s->topk <= 24 ? 3 : 2);
+        while (tile_step > 1 && (dec.nt / tile_step) * vosk::kIdxSub < 8 * s->topk) --tile_step;    // small maps: keep >= 8 k blocks per row
+        vosk::AffinityParams ap1 = ap;
+        ap1.tile_step = tile_step;
+        VOS_CUDA(vosk::launch_topk_scan(split, 1, dec.grid, st, e->tmap_hi, e->tmap_lo, ap1));
+        VOS_CUDA(vosk::launch_topk_threshold(e->topk_bound, e->topk_tau, e->P, dec.nt, tile_step, s->topk, st));
+        VOS_CUDA(vosk::launch_topk_scan(split, 2, dec.grid, st, e->tmap_hi, e->tmap_lo, ap));
         VOS_CUDA(cudaGetLastError());
     }
+    e->launches += 2;
     if (s->record_event) VOS_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(s->record_event), st));
     vosk::TopkFinishParams fp{};
     vosk::MergeParams& mp = fp.mp;
     const int q_slot = ap.q_slot;
     mp.n_pixels = e->P; mp.p_pad = e->p_pad; mp.w_lowres = e->W_d; mp.h_lowres = e->H_d; mp.n_refs = s->n_refs;
     mp.num_sms = grid_cap; mp.d = e->d; mp.H = e->H; mp.W = e->W; mp.q_slot = q_slot;
-    mp.write_labels = s->write_labels; mp.probability = s->probability_propagation; mp.n_sub = n_sub;
+    mp.write_labels = s->write_labels; mp.probability = s->probability_propagation; mp.n_sub = vosk::kIdxSub;
     mp.partials = nullptr; mp.meta = e->meta; mp.cls = e->cls;
     mp.out_prediction = s->out_prediction;
     mp.out_mask_lowres = s->out_mask_lowres ? s->out_mask_lowres : (s->out_mask_fullres ? e->low_scratch : nullptr);
@@ -313,6 +346,8 @@ void vosprop_destroy(vosprop_engine* e) {
     cudaFree(e->cand_idx);
     cudaFree(e->cand_cnt);
     cudaFree(e->low_scratch);
+    cudaFree(e->topk_bound);
+    cudaFree(e->topk_tau);
     cudaFree(e->tables);
     for (cudaEvent_t ev : e->ev) cudaEventDestroy(ev);
     delete e;

@@ -115,7 +115,8 @@ def test_ref_num_below_three_raises_like_the_reference():
 def test_1080p_pixel_blocks_against_oracle(topk):
     """1080p: 135 x 240 = 32 400 pixels, 254 tiles (the last one 16 pixels wide), N = 291 600 at R = 9.  The full
     product is too large for a CPU test, so the oracle evaluates blocks of target pixels (each target pixel is an
-    independent softmax): the first tile, a block across a tile boundary in the middle, and the ragged tail."""
+    independent softmax): the first 2 048 pixels, 1 024 across a tile boundary in the middle and the ragged tail --
+    4 096 pixels, arg-max agreement >= 99.9 % with every disagreement a documented near tie."""
     from vosb200 import PREC_F16, plan_refs
     T, t = 10, 9
     feats, first = O.synthetic_sequence(T, 1080, 1920, 3, seed=37, feat_scale=0.30)
@@ -125,9 +126,10 @@ def test_1080p_pixel_blocks_against_oracle(topk):
     assert (H_d, W_d) == (135, 240)
     low, d = O.first_frame_labels(first)
     g = torch.Generator().manual_seed(3)
-    cls = torch.randint(0, d, (T, P), generator=g)
+    # label history: 8 x 8 blocks of one class each (mask-like), different in every frame
+    cls = torch.randint(0, d, (T, (H_d + 7) // 8, (W_d + 7) // 8), generator=g).repeat_interleave(8, 1).repeat_interleave(8, 2)
+    cls = cls[:, :H_d, :W_d].reshape(T, P).contiguous()
     cls[0] = low
-    cls[2::2] = torch.where(torch.rand(T, P, generator=g)[2::2] < 0.98, cls[2::2] * 0, cls[2::2])   # mostly homogeneous frames
     hist = torch.stack([O.index_to_onehot(cls[f], d) for f in range(T)], 1)
     eng = _engine(P, ring_slots=12)
     eng.reset(H_d, W_d, 1080, 1920, d, PREC_F16)
@@ -138,19 +140,28 @@ def test_1080p_pixel_blocks_against_oracle(topk):
     refs, sig = plan_refs(t, 40, 9, 8.0, 21.0, False)
     out = eng.propagate(t, refs, sig, 1.0, False, write_labels=False, topk=topk, want_topk_idx=topk > 0)
     got = out['prediction'].cpu()
-    for (p0, p1) in ((0, 160), (16200 - 96, 16200 + 96), (P - 144, P)):
-        res = O.predict(feats[:t], feats[t], hist[:, :t], 8.0, 21.0, t, 40, 9, 1.0, False, chunk=96,
+    n_pix = n_same = n_tie = 0
+    for (p0, p1) in ((0, 2048), (16256 - 512, 16256 + 512), (P - 1024, P)):
+        res = O.predict(feats[:t], feats[t], hist[:, :t], 8.0, 21.0, t, 40, 9, 1.0, False, chunk=512,
                         topk=topk or None, return_topk_idx=topk > 0, pixel_range=(p0, p1))
         want = res[0] if topk else res
-        err = float((got[:, p0:p1] - want).abs().max())
-        agree = float((got[:, p0:p1].argmax(0) == want.argmax(0)).float().mean())
-        print(f'1080p topk={topk} pixels [{p0},{p1}): max |dP| {err:.3e}, argmax agreement {agree:.6f}')
-        if topk:
-            same_set = (out['topk_idx'].cpu().long()[p0:p1].sort(1).values == res[1].sort(1).values).all(1)
-            assert float(same_set.float().mean()) >= 0.98
-            assert float((got[:, p0:p1] - want).abs()[:, same_set].max()) <= PROB_ATOL
-        else:
-            assert err <= PROB_ATOL and agree >= 0.99
+        keep = torch.ones(p1 - p0, dtype=torch.bool)
+        if topk:      # a near tie across the k-th boundary changes one member of the set: compared where the sets are equal
+            keep = (out['topk_idx'].cpu().long()[p0:p1].sort(1).values == res[1].sort(1).values).all(1)
+            assert float(keep.float().mean()) >= 0.99
+        err = float((got[:, p0:p1] - want).abs()[:, keep].max())
+        same = (got[:, p0:p1].argmax(0) == want.argmax(0))[keep]
+        top2 = want.topk(2, 0).values
+        near_tie = ((top2[0] - top2[1]) < 2e-3)[keep]
+        assert bool((same | near_tie).all()), 'arg-max differs where the two best classes are not a near tie'
+        n_pix += int(keep.sum()); n_same += int(same.sum()); n_tie += int((~same).sum())
+        print(f'1080p topk={topk} pixels [{p0},{p1}): max |dP| {err:.3e}, argmax agreement {float(same.float().mean()):.6f}')
+        assert err <= PROB_ATOL
+    print(f'1080p topk={topk}: {n_pix} pixels, agreement {n_same / n_pix:.6f}, {n_tie} near-tie flips')
+    # full softmax: the 99.9 % bar.  top-k with sigma = 8 at 1080p: where all k references lie far from the target pixel every
+    # class probability is below ~1e-30 and the arg-max is taken among numbers at the edge of fp32 (the GPU flushes
+    # denormals, torch on the CPU keeps them): those pixels are near ties by the rule above and the only ones that flip
+    assert n_pix >= (4096 if not topk else 4000) and n_same / n_pix >= (MASK_AGREE if not topk else 0.98)
     full = O.upsample_mask(out['mask_lowres'].cpu().long(), H_d, W_d, 1080, 1920)
     assert torch.equal(out['mask'].cpu().long(), full)
 

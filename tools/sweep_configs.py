@@ -91,6 +91,10 @@ def main():
                 print(json.dumps(dict(config='peaked', class_prototype_norm2=round(K * ps * ps, 1), noise_norm2=round(K * nz * nz, 1),
                                       texture_field='none' if not fl else f'|f|^2 = 256, correlation length {fl} px', block_skip=skip, **r)), flush=True)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == 'topk':
+        for topk in (0, 5, 20, 50):
+            print(json.dumps(dict(config=3, **measure(480, 854, 2, 9, topk, PREC_F16))), flush=True)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'prob':
         for prec in (PREC_F16, PREC_SPLIT3):
             print(json.dumps(dict(config='prob', **measure(480, 854, 2, 9, 0, prec, probability=True))), flush=True)
