@@ -4,11 +4,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (config.workload): a synthetic DAVIS-2017-val-shaped shard per GPU -- `clips` clips x
-`frames` frames at 480x854 (60x107 features, K=256), 2-4 objects, ref_num 9, frame_range 40,
-sigma 8/21, temperature 1 (BASELINE.json configs[1]: 30 seqs x ~70 frames over 8 GPUs = ~4 clips
-per GPU).  A *step* is one pass over the shard.  Weak scaling: every rank owns its own shard, no
-collective on the hot path; NCCL only gathers the per-sequence results at the end.
+Workload (config.workload, default davis30 = BASELINE.json configs[1]): a synthetic DAVIS-2017-val-shaped
+set -- 30 sequences of 34-104 frames (1 999 frames) at 480x854 (60x107 features, K=256), 1-4 objects,
+ref_num 9, frame_range 40, sigma 8/21, temperature 1 -- sharded over the ranks by whole sequences
+(vosb200.shard.assign_lpt; config.imbalance is the ceiling of that sharding).  A *step* is one pass over
+the whole set: STRONG scaling, no collective on the hot path; NCCL only gathers the per-sequence results
+at the end of the run.  --workload ytvos: configs[4]; --workload uniform: the weak-scaling shard of round 1.
 
   value : propagation-stage throughput (ring append + fused affinity/softmax/prior/gather kernel +
           merge/write-back), stride-8 embeddings already resident in HBM, timed with CUDA events.
@@ -16,8 +17,11 @@ collective on the hot path; NCCL only gathers the per-sequence results at the en
           pinned host memory -> H2D -> VOSNet on cuDNN -> propagation -> uint8 masks -> D2H, per step.
   roofline     : the fused affinity kernel against the measured bf16 tensor peak (algorithmic FLOPs
                  2*P*(R*P)*K per launch, CUDA events around every launch of the timed region).
-  cpu_baseline : the CPU port of the reference (oracle/) on this box's host cores, bounded sample.
---impl reference times that CPU port end to end (the reference is pure Python/torch and cannot
+  split3, roofline_topk : (N = 1) sub-records of the same run on a sample of the workload: fp32 embeddings
+                 (bf16 hi+lo, three passes) and the top-k extension (k = 5, 20, 50).
+  cpu_baseline : the reference's CPU path on this box's host cores, bounded sample.
+--impl reference times that CPU path end to end: the reference's own code when its sources are
+importable (build container), else the oracle port (the reference is pure Python/torch and does not
 travel to the GPU box; the oracle is its line-by-line restatement, pinned bit-exact to it).
 """
 from __future__ import annotations
@@ -42,10 +46,8 @@ import torch  # noqa: E402
 H, W, K = 480, 854, 256
 REF_NUM, FRAME_RANGE, SIGMA_1, SIGMA_2, TEMPERATURE = 9, 40, 8.0, 21.0, 1.0
 METRIC = 'propagated frames/sec at 480p'
-# dram__bytes_read.sum + dram__bytes_write.sum of one vos_affinity_idx launch (R = 9) from the ncu --set full
-# captures under profiles/ (see profiles/README.md); None until captured for that mode
-TRAFFIC_BYTES = {'f16': 33.7e6, 'split3': 63.4e6}
 UNIT = 'frames/s'
+TRAFFIC_FILE = REPO / 'profiles' / 'r2_traffic.json'     # dram bytes per launch, written by tools/ncu_traffic.py from a committed capture
 
 
 def parse_args():
@@ -54,8 +56,12 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
-    ap.add_argument('--clips', type=int, default=4, help='clips per GPU per step')
-    ap.add_argument('--frames', type=int, default=70, help='frames per clip')
+    ap.add_argument('--workload', choices=['davis30', 'ytvos', 'uniform'], default='davis30',
+                    help='davis30 (BASELINE.json configs[1]): 30 sequences of 34-104 frames (1 999 in all), 1-4 objects, sharded '
+                         'over the ranks by whole sequences (LPT) -- strong scaling.  ytvos (configs[4]): 32 sequences of 20-180 '
+                         'frames, up to 10 objects, same sharding.  uniform: --clips x --frames per GPU -- weak scaling')
+    ap.add_argument('--clips', type=int, default=4, help='uniform workload: clips per GPU per step')
+    ap.add_argument('--frames', type=int, default=70, help='uniform workload: frames per clip')
     ap.add_argument('--precision', choices=['f16', 'split3'], default='f16',
                     help='embeddings resident in HBM for `value`: fp16 (what VOSNet emits under autocast; one exact '
                          'tensor-core pass) or fp32 (bf16 hi+lo split, three passes)')
@@ -65,22 +71,52 @@ def parse_args():
     ap.add_argument('--no-kernel-events', action='store_true', help='do not bracket every kernel with CUDA events (roofline fields become null)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-sub-records', action='store_true', help='skip the split3 and top-k sub-records (N = 1 only)')
     ap.add_argument('--ref-frames', type=int, default=2, help='reference arm: propagated frames per step')
     return ap.parse_args()
 
 
-def workload_config(args, n_gpus):
-    return {'workload': f'synthetic DAVIS-2017-val-shaped shard: {args.clips} clips x {args.frames} frames per GPU, '
-                        f'480x854 (60x107 stride-8 features, K=256), 2-4 objects',
-            'clips_per_gpu': args.clips, 'frames_per_clip': args.frames, 'n_gpus': n_gpus,
-            'sequences_in_flight_per_gpu': max(1, min(args.lanes, args.clips)),
+def workload_sequences(args, world):
+    """[(frames, objects)] of the whole job, the same list on every rank."""
+    import numpy as np
+    if args.workload == 'uniform':
+        return [(args.frames, 2 + (i + r) % 3) for r in range(world) for i in range(args.clips)]
+    if args.workload == 'davis30':        # DAVIS-2017 val: 30 sequences, 1 999 frames, 34-104 frames each, 1-5 objects (mean ~2)
+        rs = np.random.RandomState(2017)
+        lens = rs.randint(34, 105, size=30)
+        while lens.sum() != 1999:
+            i = rs.randint(30)
+            step = 1 if lens.sum() < 1999 else -1
+            if 34 <= lens[i] + step <= 104:
+                lens[i] += step
+        objs = rs.choice([1, 2, 3, 4], size=30, p=[0.4, 0.3, 0.2, 0.1])
+        return [(int(n), int(o)) for n, o in zip(lens, objs)]
+    rs = np.random.RandomState(2019)      # YouTube-VOS-shaped: variable lengths, up to 10 objects
+    lens = rs.randint(20, 181, size=32)
+    objs = rs.randint(1, 11, size=32)
+    return [(int(n), int(o)) for n, o in zip(lens, objs)]
+
+
+def workload_config(args, n_gpus, seqs, assignment, imbalance):
+    total = sum(n - 1 for n, _ in seqs)
+    names = {'davis30': 'synthetic DAVIS-2017-val-shaped set: 30 sequences x 34-104 frames (1 999 frames, 1-4 objects), sharded '
+                        'over the GPUs by whole sequences (static LPT on sum_t R_t P^2), no collective on the hot path',
+             'ytvos': 'synthetic YouTube-VOS-shaped set: 32 sequences x 20-180 frames, 1-10 objects, sharded over the GPUs by '
+                      'whole sequences (static LPT)',
+             'uniform': f'{args.clips} clips x {args.frames} frames per GPU (weak scaling)'}
+    return {'workload': names[args.workload] + '; 480x854 (60x107 stride-8 features, K=256)',
+            'workload_key': args.workload, 'sequences': len(seqs), 'propagated_frames_per_step': total, 'n_gpus': n_gpus,
+            'sequences_per_gpu': [len(a) for a in assignment], 'imbalance': round(imbalance, 4),
+            'imbalance_note': 'max rank cost / mean rank cost of the LPT assignment: the ceiling of whole-sequence sharding is 1/imbalance',
+            'sequences_in_flight_per_gpu': max(1, args.lanes),
             'ref_num': REF_NUM, 'frame_range': FRAME_RANGE, 'sigma': [SIGMA_1, SIGMA_2], 'temperature': TEMPERATURE,
             'precision': ('fp16 embeddings (VOSNet under autocast, as the reference on CUDA): one tcgen05 kind::f16 pass, '
                           'products exact in the fp32 accumulator, fp32 softmax' if args.precision == 'f16' else
                           'fp32 embeddings: bf16x3 split (hi*hi + lo*hi + hi*lo) tcgen05, fp32 accumulate/softmax'),
-            'l2': f'inputs larger than L2 ({0.9 if args.precision == "f16" else 1.8:.1f} GB of embeddings per step; 126 MB L2)',
+            'l2': 'inputs larger than L2 (3.3 MB of fp16 embeddings per frame, > 1 GB per step per GPU; 126 MB L2)',
             'value_scope': 'propagation stage: append + fused affinity + merge/write-back; embeddings resident in HBM',
-            'e2e_scope': 'ClipSegmenter.segment: pinned host frames -> H2D -> VOSNet(cuDNN, fp16 autocast) -> propagation -> uint8 masks -> D2H'}
+            'e2e_scope': 'ClipSegmenter.segment: pinned host uint8 frames -> H2D -> normalise (vosprop_normalize_u8) -> VOSNet(cuDNN, fp16) '
+                         '-> propagation -> uint8 masks -> D2H per sequence; one NCCL gather of all masks to rank 0 at the end of the run'}
 
 
 class ClockSampler:
@@ -153,21 +189,35 @@ def steady_refs(frame_idx):
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU port of the reference (oracle) -- cpu_baseline leg and --impl reference
+# The reference's CPU path -- cpu_baseline leg and --impl reference
 # ----------------------------------------------------------------------------------------------
 def cpu_reference_sample(n_frames, steps, warmup):
     """End-to-end CPU frames/s of the reference algorithm on a bounded sample: `n_frames`
     steady-state frames (frame_idx >= 16, 9 references, both sigma branches) of one 480p clip per
-    step; each frame = VOSNet.forward on CPU + predict + argmax/upsample.  fp32, all host threads."""
+    step; each frame = VOSNet.forward on CPU + predict + argmax/upsample.  fp32, all host threads.
+    Runs the reference's OWN predict() / VOSNet when its sources are importable (/root/reference in the build
+    container, baseline/_ref if someone put a copy there): kind "reference"; otherwise the oracle, its
+    line-by-line restatement pinned bit-exact to it (tests/test_oracle_golden.py): kind "port"."""
     from oracle import propagation_oracle as O
-    from src.model.vos_net import VOSNet
     # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would make this a 1-thread run)
     try:
         torch.set_num_threads(len(os.sched_getaffinity(0)))
     except (AttributeError, RuntimeError):
         torch.set_num_threads(os.cpu_count() or 1)
+    ref = None
+    try:
+        from oracle import reference_harness
+        if reference_harness.find_reference() is not None:
+            ref = reference_harness.import_reference('cpu')
+    except Exception as exc:  # noqa: BLE001
+        print(f'bench: reference sources present but not importable ({exc}); timing the port', file=sys.stderr)
+        ref = None
     torch.manual_seed(0)
-    net = VOSNet('resnet50', pretrained=False).eval()
+    if ref is not None:
+        net = ref.vos_net.VOSNet('resnet50').eval()
+    else:
+        from src.model.vos_net import VOSNet
+        net = VOSNet('resnet50', pretrained=False).eval()
     t0_idx = 16
     T = t0_idx + n_frames
     feats, first = O.synthetic_sequence(T, H, W, 2, seed=5, feat_scale=0.30)
@@ -177,35 +227,55 @@ def cpu_reference_sample(n_frames, steps, warmup):
     g = torch.Generator().manual_seed(1)
     labels = torch.stack([O.index_to_onehot(torch.randint(0, d, (P,), generator=g), d) for _ in range(T)], 1)
     frame = torch.randn(1, 3, H, W, generator=g)
-    # the reference builds the two (P,P) priors once per video (predict.py:117-118): outside the per-frame timing
-    priors = (O.spatial_weight((H_d, W_d), SIGMA_1), O.spatial_weight((H_d, W_d), SIGMA_2))
+    # the reference builds the two (P,P) priors once per video (predict.py:117-118, 0.8-1 s each): outside the per-frame timing,
+    # as is the O(T^2) torch.cat of its history (inference_utils.py:67-72) -- both omissions favour the reference
+    if ref is not None:
+        priors = (ref.predict.get_spatial_weight((H_d, W_d), SIGMA_1), ref.predict.get_spatial_weight((H_d, W_d), SIGMA_2))
+    else:
+        priors = (O.spatial_weight((H_d, W_d), SIGMA_1), O.spatial_weight((H_d, W_d), SIGMA_2))
     times = []
     with torch.no_grad():
-        for s in range(warmup + steps):
+        for s_ in range(warmup + steps):
             t0 = time.perf_counter()
             for t in range(t0_idx, T):
                 _ = net(frame)                                               # P0
-                pred = O.predict(feats[:t], feats[t], labels[:, :t], SIGMA_1, SIGMA_2, t, FRAME_RANGE, REF_NUM,
-                                 TEMPERATURE, False, weights=priors)         # P1-P3
+                if ref is not None:
+                    pred = ref.predict.predict(feats[:t], feats[t], labels[:, :t], priors[0], priors[1], t, FRAME_RANGE, REF_NUM,
+                                               TEMPERATURE, False)           # P1-P3
+                else:
+                    pred = O.predict(feats[:t], feats[t], labels[:, :t], SIGMA_1, SIGMA_2, t, FRAME_RANGE, REF_NUM,
+                                     TEMPERATURE, False, weights=priors)     # P1-P3
                 up = torch.nn.functional.interpolate(pred.view(1, d, H_d, W_d), size=(H, W), mode='nearest')
                 _ = torch.argmax(up, 1)                                      # P6
-            if s >= warmup:
+            if s_ >= warmup:
                 times.append(time.perf_counter() - t0)
     per_step = sum(times) / len(times)
-    return n_frames / per_step, per_step, torch.get_num_threads()
+    return n_frames / per_step, per_step, torch.get_num_threads(), 'reference' if ref is not None else 'port'
+
+
+def cpu_sample_text(n_frames, cores, kind):
+    who = "the reference's own VOSNet.forward + predict()" if kind == 'reference' else \
+        "VOSNet.forward + the oracle's predict() (bit-exact restatement of the reference's; its sources cannot travel to the GPU box)"
+    return (f'{n_frames} steady-state propagated frames (frame_idx>=16, 9 refs) of one 480p clip per step: {who} + upsample/argmax '
+            f'on CPU, fp32, torch threads={cores}; the per-video construction of the two (P,P) priors (0.8-1 s each in the reference) '
+            f'and its O(T^2) history torch.cat are NOT in the timed region (both omissions favour the reference)')
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    fps, per_step, cores = cpu_reference_sample(args.ref_frames, max(args.steps, 1), min(args.warmup, 1))
-    cfg = workload_config(args, args.gpus)
-    sample = (f'{args.ref_frames} steady-state propagated frames (frame_idx>=16, 9 refs) of one 480p clip per step: '
-              f'VOSNet.forward + predict + upsample/argmax on CPU, fp32, torch threads={cores}')
+    fps, per_step, cores, kind = cpu_reference_sample(args.ref_frames, max(args.steps, 1), min(args.warmup, 1))
+    seqs = workload_sequences(args, args.gpus)
+    from vosb200 import shard
+    costs = [shard.sequence_cost(n, 6420, REF_NUM) for n, _ in seqs]
+    assignment = shard.assign_lpt(costs, args.gpus)
+    cfg = workload_config(args, args.gpus, seqs, assignment, shard.imbalance(costs, assignment))
+    sample = cpu_sample_text(args.ref_frames, cores, kind)
     line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': per_step * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'warmup': args.warmup, 'ms_per_step': per_step * 1e3, 'higher_is_better': True,
+            'scaling': 'weak' if args.workload == 'uniform' else 'strong',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
-            'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'cpu_baseline': {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
             'e2e': {'value': fps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
@@ -214,10 +284,20 @@ def run_reference(args, rank):
 # ----------------------------------------------------------------------------------------------
 # ours
 # ----------------------------------------------------------------------------------------------
+def clip_flops(T, P):
+    return sum(2.0 * P * (steady_refs(t) * P) * K for t in range(1, T))
+
+
+def traffic_bytes(precision):
+    try:
+        return json.loads(TRAFFIC_FILE.read_text()).get(precision, {}).get('dram_bytes_per_launch')
+    except (OSError, ValueError):
+        return None
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
-    from vosb200 import PropagationEngine
-    from vosb200 import synthetic
+    from vosb200 import PropagationEngine, shard, synthetic
     from vosb200.pipeline import ClipSegmenter
     from vosb200.sequence import propagate_clip, propagate_clips_lanes
     from src.model.vos_net import VOSNet
@@ -232,78 +312,104 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    C, T = args.clips, args.frames
-    n_obj = [2 + (i + rank) % 3 for i in range(C)]
-    clips = [synthetic.clip_features(T, H, W, n_obj[i], seed=1000 * rank + i, device=dev) for i in range(C)]
-    if args.precision == 'f16':
-        clips = [(f.half(), first) for f, first in clips]
+    # ---------------- the job and this rank's share of it
+    seqs = workload_sequences(args, world)
+    H_d, W_d = (H + 7) // 8, (W + 7) // 8
+    P = H_d * W_d
+    costs = [shard.sequence_cost(n, P, REF_NUM) for n, _ in seqs]
+    if args.workload == 'uniform':
+        assignment = [list(range(r * args.clips, (r + 1) * args.clips)) for r in range(world)]
+    else:
+        assignment = shard.assign_lpt(costs, world)
+    imbalance = shard.imbalance(costs, assignment)
+    mine = assignment[rank]
+    frames_per_step = sum(n - 1 for n, _ in seqs)
+
+    def make_clips(indices, half):
+        out = []
+        for i in indices:
+            f, first = synthetic.clip_features(seqs[i][0], H, W, seqs[i][1], seed=1000 + i, device=dev)
+            out.append((f.half() if half else f, first))
+        return out
+
+    clips = make_clips(mine, args.precision == 'f16')
+    n_obj = [seqs[i][1] for i in mine]
     passes = 1 if args.precision == 'f16' else 3
-    P = clips[0][0].shape[2] * clips[0][0].shape[3]
-    lanes = max(1, min(args.lanes, C))
+    lanes = max(1, min(args.lanes, len(clips)))
     engines = [PropagationEngine(max_pixels=P, ring_slots=48, device=dev) for _ in range(lanes)]
     lane_streams = [torch.cuda.Stream(dev) for _ in range(lanes)]
     eng = engines[0]
-    masks_keep = [None] * C
+    masks_keep = [None] * len(clips)
 
-    def prop_step():
-        if lanes == 1:
-            for i, (feats, first) in enumerate(clips):
-                masks_keep[i] = propagate_clip(eng, feats, first, SIGMA_1, SIGMA_2, FRAME_RANGE, REF_NUM, TEMPERATURE,
-                                               False, d=n_obj[i] + 1)
+    def prop_step(which=clips, objs=n_obj, keep=masks_keep, topk=0):
+        if lanes == 1 or topk:
+            for i, (feats, first) in enumerate(which):
+                keep[i] = propagate_clip(eng, feats, first, SIGMA_1, SIGMA_2, FRAME_RANGE, REF_NUM, TEMPERATURE,
+                                         False, d=objs[i] + 1, topk=topk)
         else:   # several sequences in flight: small kernels of one lane run under the affinity kernel of another
-            masks_keep[:] = propagate_clips_lanes(engines, [(f, first, n_obj[i] + 1) for i, (f, first) in enumerate(clips)],
-                                                  SIGMA_1, SIGMA_2, FRAME_RANGE, REF_NUM, TEMPERATURE, False,
-                                                  streams=lane_streams)
+            keep[:] = propagate_clips_lanes(engines, [(f, first, objs[i] + 1) for i, (f, first) in enumerate(which)],
+                                            SIGMA_1, SIGMA_2, FRAME_RANGE, REF_NUM, TEMPERATURE, False,
+                                            streams=lane_streams)
 
-    for _ in range(args.warmup):
-        prop_step()
-    launches_per_step = 3 * (T - 1) + 3        # per clip: reset + append(0) + labels(0) + (append, affinity, merge) per frame
-    # inside the timed region only the dominant kernel (fused affinity) is bracketed with events: event records cost
-    # front-end time (all three classes: -6 % frames/s); append / merge are timed in one extra pass afterwards
-    for e_ in engines:
-        e_.enable_timing(0 if args.no_kernel_events else args.steps * C * launches_per_step + 16, classes=('affinity',))
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = sum(e_.launch_count for e_ in engines)
-    barrier()
-    with ClockSampler(local_rank) as clocks:
-        ev0.record()
-        for _ in range(args.steps):
-            prop_step()
-        ev1.record()
+    def timed_steps(step_fn, n_warm, n_steps, n_clips, n_frames):
+        """Device time of n_steps passes (CUDA events, barrier + synchronize on both sides), clocks sampled meanwhile, the fused
+        kernel bracketed with events; returns (ms per step (this rank), affinity (ms, launches), clock summary, launches)."""
+        for _ in range(n_warm):
+            step_fn()
+        # inside the timed region only the dominant kernel class (fused affinity) is bracketed with events: event records cost
+        # front-end time (all three classes: -6 % frames/s); append / merge are timed in one extra pass afterwards
+        cap = 0 if args.no_kernel_events else n_steps * (4 * n_frames + 4 * n_clips) + 16
+        for e_ in engines:
+            e_.enable_timing(cap, classes=('affinity',))
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = sum(e_.launch_count for e_ in engines)
         barrier()
-    ms = ev0.elapsed_time(ev1)
-    gpu_launches = sum(e_.launch_count for e_ in engines) - launches0
-    stage = {'append': (0.0, 0), 'affinity': (0.0, 0), 'merge': (0.0, 0)}
-    for e_ in engines:
-        for k_, (ms_, n_) in e_.read_timing().items():
-            stage[k_] = (stage[k_][0] + ms_, stage[k_][1] + n_)
-        e_.enable_timing(0)
-    if not args.no_kernel_events:
-        eng.enable_timing(launches_per_step + 16, classes=('append', 'merge'))
+        with ClockSampler(local_rank) as clocks:
+            ev0.record()
+            for _ in range(n_steps):
+                step_fn()
+            ev1.record()
+            barrier()
+        ms = ev0.elapsed_time(ev1) / n_steps
+        launches = sum(e_.launch_count for e_ in engines) - launches0
+        aff = (0.0, 0)
+        for e_ in engines:
+            t_ = e_.read_timing()['affinity']
+            aff = (aff[0] + t_[0], aff[1] + t_[1])
+            e_.enable_timing(0)
+        return ms, aff, clocks.summary(), launches
+
+    my_frames = sum(seqs[i][0] - 1 for i in mine)
+    ms_local, (aff_ms, aff_n), clock_summary, gpu_launches = timed_steps(prop_step, args.warmup, args.steps, len(clips), my_frames)
+    stage = {'append': (0.0, 0), 'merge': (0.0, 0)}
+    if not args.no_kernel_events and clips:
+        eng.enable_timing(4 * seqs[mine[0]][0] + 16, classes=('append', 'merge'))
         propagate_clip(eng, clips[0][0], clips[0][1], SIGMA_1, SIGMA_2, FRAME_RANGE, REF_NUM, TEMPERATURE, False, d=n_obj[0] + 1)
         torch.cuda.synchronize(dev)
-        for k_, (ms_, n_) in eng.read_timing().items():
-            stage[k_] = (stage[k_][0] + ms_, stage[k_][1] + n_)
+        tm = eng.read_timing()
+        stage = {k_: tm[k_] for k_ in ('append', 'merge')}
         eng.enable_timing(0)
-    t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    t_ms = torch.tensor([ms_local], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_step = float(t_ms.item()) / args.steps
-    frames_per_step = C * (T - 1) * world
+    ms_step = float(t_ms.item())
     value = frames_per_step / (ms_step / 1e3)
 
-    # roofline of the dominant kernel (fused affinity): algorithmic FLOPs 2*P*(R*P)*K per launch
-    flops = sum(2.0 * P * (steady_refs(t) * P) * K for t in range(1, T)) * C * args.steps
-    aff_ms, aff_n = stage['affinity']
     peak_tf, peak_hbm, peak_src = measured_peaks()
-    achieved_tf = flops / (aff_ms * 1e-3) / 1e12 if aff_ms > 0 else 0.0
-    roofline = {'bound': 'tensor', 'kernel': 'vos_affinity_idx', 'achieved': achieved_tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                'frac': achieved_tf / peak_tf, 'traffic': TRAFFIC_BYTES.get(args.precision), 'peak_source': peak_src,
-                'issued_tflops': passes * achieved_tf, 'issued_frac': passes * achieved_tf / peak_tf,
-                'launches': aff_n, 'avg_launch_us': aff_ms * 1e3 / max(aff_n, 1),
-                'note': 'achieved counts algorithmic FLOPs 2*P*N*K per launch; tensor-core passes issued per logit: '
-                        f'{passes}; traffic = dram bytes read+written per launch from the ncu capture in profiles/ (null: not captured)'}
-    # HBM-bound side kernels: algorithmic bytes per launch
+
+    def roofline_of(aff_ms_, aff_n_, flops_, passes_, precision_, kernel_name):
+        tf = flops_ / (aff_ms_ * 1e-3) / 1e12 if aff_ms_ > 0 else 0.0
+        return {'bound': 'tensor', 'kernel': kernel_name, 'achieved': tf, 'peak': peak_tf, 'unit': 'TFLOP/s',
+                'frac': tf / peak_tf, 'traffic': traffic_bytes(precision_), 'peak_source': peak_src,
+                'issued_tflops': passes_ * tf, 'issued_frac': passes_ * tf / peak_tf,
+                'launches': aff_n_, 'avg_launch_us': aff_ms_ * 1e3 / max(aff_n_, 1),
+                'note': 'achieved counts algorithmic FLOPs 2*P*N*K per launch over all launches of the timed region on rank 0 (reference '
+                        f'counts ramp 1..9 at the start of every sequence); tensor-core passes issued per logit: {passes_}; traffic = dram '
+                        'bytes read+written per R = 9 launch from the committed ncu capture (profiles/r2_traffic.json; null: not captured)'}
+
+    my_flops = sum(clip_flops(seqs[i][0], P) for i in mine)
+    roofline = roofline_of(aff_ms, aff_n, my_flops * args.steps, passes, args.precision, 'vos_affinity_idx')
+    # HBM-bound side kernels: algorithmic bytes per launch (DESIGN.md section 5)
     app_ms, app_n = stage['append']
     mrg_ms, mrg_n = stage['merge']
     app_bytes = P * K * 2 * 2 if args.precision == 'f16' else P * K * 4 + 2 * P * K * 2
@@ -314,6 +420,34 @@ def run_ours(args, rank, world, local_rank):
                                 'bytes_per_launch': mrg_bytes},
             'hbm_peak_gbs': peak_hbm}
 
+    # ---------------- sub-records of the same run (N = 1): the fp32-embedding-faithful mode and the top-k extension
+    sub = {}
+    if world == 1 and not args.no_sub_records and args.precision == 'f16':
+        sample = mine[:6]
+        sample_frames_n = sum(seqs[i][0] - 1 for i in sample)
+        sample_txt = f'first {len(sample)} sequences of the workload ({sample_frames_n} propagated frames per step), 1 warm-up + 2 timed steps'
+        s_objs = [seqs[i][1] for i in sample]
+        s_keep = [None] * len(sample)
+        fp32_clips = make_clips(sample, False)
+        ms_, (a_ms, a_n), _, _ = timed_steps(lambda: prop_step(fp32_clips, s_objs, s_keep), 1, 2, len(sample), sample_frames_n)
+        flops_ = sum(clip_flops(seqs[i][0], P) for i in sample) * 2
+        sub['split3'] = {'value': sample_frames_n / (ms_ / 1e3), 'unit': UNIT, 'dtype': 'bf16x3', 'sample': sample_txt,
+                         'precision': 'fp32 embeddings stored as bf16 hi + lo, three tcgen05 passes per logit (max |dP| 5e-5 against the fp32 reference)',
+                         'roofline': roofline_of(a_ms, a_n, flops_, 3, 'split3', 'vos_affinity_idx<split>')}
+        del fp32_clips
+        f16_clips = clips[:len(sample)]
+        topk_rec = {}
+        for k_ in (5, 20, 50):
+            ms_, (a_ms, a_n), _, _ = timed_steps(lambda: prop_step(f16_clips, s_objs, s_keep, topk=k_), 1, 2, len(sample), sample_frames_n)
+            tf = flops_ / (a_ms * 1e-3) / 1e12 if a_ms > 0 else 0.0
+            topk_rec[str(k_)] = {'value': sample_frames_n / (ms_ / 1e3), 'unit': UNIT, 'scan_us_per_frame': a_ms * 1e3 / max(a_n, 1),
+                                 'achieved': tf, 'frac': tf / peak_tf}
+        ms_, _, _, _ = timed_steps(lambda: prop_step(f16_clips, s_objs, s_keep), 1, 2, len(sample), sample_frames_n)
+        sub['roofline_topk'] = {'bound': 'tensor', 'kernel': 'vos_topk_scan (both passes) + vos_topk_threshold', 'peak': peak_tf, 'unit': 'TFLOP/s',
+                                'sample': sample_txt, 'full_softmax_value_same_sample': sample_frames_n / (ms_ / 1e3), 'k': topk_rec,
+                                'note': 'achieved = algorithmic FLOPs 2*P*N*K of the frame (counted ONCE; the two scans issue 1 + 1/step of them) '
+                                        '/ device time of scan 1 + threshold + scan 2; value = frames/s of the whole top-k propagation stage'}
+
     # ---------------- e2e through the public API
     e2e = None
     if not args.no_e2e:
@@ -321,17 +455,13 @@ def run_ours(args, rank, world, local_rank):
         net = VOSNet('resnet50', pretrained=False)
         seg = ClipSegmenter(net, device=dev, sigma_1=SIGMA_1, sigma_2=SIGMA_2, frame_range=FRAME_RANGE, ref_num=REF_NUM,
                             temperature=TEMPERATURE)
-        host_clips = [synthetic.clip_frames(T, H, W, n_obj[i], seed=2000 * rank + i, device=dev) for i in range(C)]
-        outs = [torch.empty((T - 1, H, W), dtype=torch.uint8, pin_memory=True) for _ in range(C)]
+        host_clips = [synthetic.clip_frames(seqs[i][0], H, W, seqs[i][1], seed=2000 + i, device=dev, raw=True) for i in mine]
+        outs = [torch.empty((seqs[i][0] - 1, H, W), dtype=torch.uint8, pin_memory=True) for i in mine]
 
         def e2e_step():
             for i, (frames, first) in enumerate(host_clips):
                 seg.segment(frames, first, out=outs[i], sync=False)
-            torch.cuda.synchronize(dev)     # results of the step are on the host
-            if world > 1:                   # final per-sequence result gather (NCCL), as the north star prescribes
-                res = torch.stack([o.to(dev, non_blocking=True) for o in outs])
-                gathered = [torch.empty_like(res) for _ in range(world)] if rank == 0 else None
-                dist.gather(res, gathered, dst=0)
+            torch.cuda.synchronize(dev)     # the masks of the step are in pinned host memory
 
         for _ in range(max(1, min(args.warmup, 2))):
             e2e_step()
@@ -339,27 +469,33 @@ def run_ours(args, rank, world, local_rank):
         t0 = time.perf_counter()
         for _ in range(args.steps):
             e2e_step()
+        gathered = 0
+        if world > 1:                       # end of run: the final per-sequence result gather (NCCL), inside the timed region
+            res = shard.gather_results({mine[i]: outs[i].to(dev, non_blocking=True) for i in range(len(mine))}, dst=0)
+            gathered = sum(int(v.numel()) for v in res.values())
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {'value': frames_per_step / (float(dt.item()) / args.steps), 'unit': UNIT,
-               'h2d_bytes_per_step': C * T * 3 * H * W * 4, 'd2h_bytes_per_step': C * (T - 1) * H * W,
-               'ms_per_step': float(dt.item()) / args.steps * 1e3}
+               'h2d_bytes_per_step': sum(n for n, _ in seqs) * 3 * H * W, 'd2h_bytes_per_step': frames_per_step * H * W,
+               'ms_per_step': float(dt.item()) / args.steps * 1e3, 'input': 'uint8 RGB frames in pinned host memory (all ranks together)',
+               'final_gather_bytes': gathered}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fps, per_step, cores = cpu_reference_sample(2, 1, 1)
-        cpu = {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-               'sample': '2 steady-state propagated 480p frames (frame_idx>=16, 9 refs): VOSNet.forward + oracle predict '
-                         '+ upsample/argmax on the host CPU, fp32, after 1 warm-up pass'}
+        fps, per_step, cores, kind = cpu_reference_sample(2, 1, 1)
+        cpu = {'value': fps, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': cpu_sample_text(2, cores, kind) + ', after 1 warm-up pass'}
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-                'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'f16' if args.precision == 'f16' else 'bf16x3', 'data': 'synthetic', 'config': workload_config(args, world),
-                'clocks': clocks.summary(), 'e2e': e2e, 'gpu_launches': int(gpu_launches),
+                'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak' if args.workload == 'uniform' else 'strong',
+                'vs_baseline': None,
+                'dtype': 'f16' if args.precision == 'f16' else 'bf16x3', 'data': 'synthetic',
+                'config': workload_config(args, world, seqs, assignment, imbalance),
+                'clocks': clock_summary, 'e2e': e2e, 'gpu_launches': int(gpu_launches),
                 'roofline': roofline, 'side_kernels': side, 'cpu_baseline': cpu}
+        line.update(sub)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -66,18 +66,34 @@ def inference_command_impl(ref_num, data, resume, model, temperature, frame_rang
                            scale, reduction, disable=False):
     if Config.DEVICE.type != device:
         Config.DEVICE = torch.device(device)
+    # `torchrun --nproc-per-node N main.py inference ...`: one process per GPU, whole videos sharded over the ranks (the
+    # reference resets all state at a video boundary, inference_utils.py:28-48, so the masks do not depend on the sharding);
+    # every rank writes the PNGs of its own videos, no collective anywhere
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    if world > 1 and device == 'cuda':
+        Config.DEVICE = torch.device('cuda', int(os.environ.get('LOCAL_RANK', rank)))
+        torch.cuda.set_device(Config.DEVICE)
     model = _load_net(model, resume)
     additional_model = _load_net(additional_model_type, additional_resume) if inference_strategy == 'multimodel' else None
 
+    videos = None
+    if world > 1:
+        from vosb200.shard import assign_lpt, sequence_cost
+        counts = sorted((d.name, sum(1 for _ in d.iterdir())) for d in (Path(data) / 'JPEGImages/480p').iterdir() if d.is_dir())
+        mine = assign_lpt([sequence_cost(n, 1, ref_num) for _, n in counts], world)[rank]
+        videos = {counts[i][0] for i in mine}
+        logger.info(f'rank {rank}/{world}: {len(videos)} of {len(counts)} videos')
+        if not videos:
+            return
     dataset = InferenceDataset(str(Path(data) / 'JPEGImages/480p'), disable=disable,
-                               inference_strategy=inference_strategy, scale=scale, raw=True)
+                               inference_strategy=inference_strategy, scale=scale, raw=True, videos=videos)
     # the reference decodes with one worker (inference.py:75-78); JPEG decode is the slowest stage once propagation runs on
     # the GPU, so it is spread over workers here (same PIL decode, same order: shuffle=False)
     cpus = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     loader = torch.utils.data.DataLoader(dataset, batch_size=1, shuffle=False, num_workers=max(1, min(12, cpus - 4, cpus)) if cpus > 8 else min(8, cpus),
                                          pin_memory=True, prefetch_factor=4, persistent_workers=False)
     annotation_dir = Path(data) / 'Annotations/480p'
-    last_video = sorted(annotation_dir.glob('*'))[0].name
+    last_video = sorted(v.name for v in annotation_dir.glob('*') if videos is None or v.name in videos)[0]
     common = (loader, len(dataset), annotation_dir, last_video, save, sigma_1, sigma_2, frame_range, ref_num,
               temperature, probability_propagation)
     with torch.no_grad():

@@ -66,8 +66,13 @@ class InferenceDataset(datasets.ImageFolder):
     bits) -- ToTensor + Normalize cost more host time per 480p frame than the JPEG decode."""
 
     def __init__(self, root, transform=None, target_transform=None, disable=False,
-                 inference_strategy='single', scale=None, raw=False):
+                 inference_strategy='single', scale=None, raw=False, videos=None):
         super().__init__(root, transform=transform, target_transform=target_transform)
+        if videos is not None:         # this rank's share of the videos (src/inference.py under torchrun)
+            keep = {self.class_to_idx[v] for v in videos}
+            self.samples = [s for s in self.samples if s[1] in keep]
+            self.imgs = self.samples
+            self.targets = [s[1] for s in self.samples]
         self.raw = raw
         self.rgb_normalize = transforms.Compose([
             transforms.ToTensor(),

@@ -1,7 +1,8 @@
 """ClipSegmenter: the library-level public call -- frames + first-frame annotation in, masks out.
 
 End-to-end path of one clip on one GPU:
-  pinned host frames --H2D (copy stream, batch ahead)--> VOSNet on cuDNN (fp16 autocast, as the
+  pinned host frames (decoded uint8 RGB, or already normalised fp32) --H2D (copy stream, batch ahead)--> normalisation on the
+  GPU for uint8 input (vosprop_normalize_u8: 4x less PCIe traffic than fp32 frames) --> VOSNet on cuDNN (fp16 autocast, as the
   reference does on CUDA: inference_utils.py:35,52; channels_last) --> per frame: ring append +
   fused propagation (libvosprop) --> uint8 masks accumulate on the device --> one D2H per clip.
 Feature extraction does not depend on propagation state, so frames go through
@@ -14,7 +15,7 @@ from typing import Optional
 import torch
 
 from . import _capi as capi
-from .engine import PropagationEngine, required_ring_slots
+from .engine import PropagationEngine, normalize_frames, required_ring_slots
 from .sequence import start_sequence
 
 
@@ -59,9 +60,14 @@ class ClipSegmenter:
     @torch.no_grad()
     def segment(self, frames: torch.Tensor, first_label: torch.Tensor, out: Optional[torch.Tensor] = None,
                 sync: bool = True) -> torch.Tensor:
-        """frames (T,3,H,W) fp32, pinned host or device; first_label (H,W) integer class map.
+        """frames: (T,H,W,3) uint8 decoded RGB (normalised on the GPU like datasets.py:128-131) or (T,3,H,W) fp32 already
+        normalised; pinned host or device.  first_label (H,W) integer class map.
         Returns masks for frames 1..T-1 as (T-1,H,W) uint8 in pinned host memory."""
-        T, _, H, W = frames.shape
+        raw = frames.dtype == torch.uint8
+        if raw:
+            T, H, W, _ = frames.shape
+        else:
+            T, _, H, W = frames.shape
         main = torch.cuda.current_stream(self.device)
         B = self.backbone_batch
         on_host = not frames.is_cuda
@@ -87,6 +93,8 @@ class ClipSegmenter:
             if on_host:
                 main.wait_event(staged.pop(b0))
                 cur.record_stream(main)
+            if raw:
+                cur = normalize_frames(cur, torch.float16 if self.amp else torch.float32)
             feats = self.embed(cur)
             for i in range(feats.shape[0]):
                 t = b0 + i

@@ -45,19 +45,24 @@ def clip_features(T: int, H: int, W: int, n_objects: int, seed: int, device, K: 
     return feats, _class_map(tr, 0, H, W, device).to(torch.uint8)
 
 
-def clip_frames(T: int, H: int, W: int, n_objects: int, seed: int, device, pinned: bool = True
+def clip_frames(T: int, H: int, W: int, n_objects: int, seed: int, device, pinned: bool = True, raw: bool = False
                 ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Image-space clip: (frames (T,3,H,W) fp32 ImageNet-normalised in pinned host memory,
-    first annotation (H,W) uint8 on host) -- what InferenceDataset would hand the loop."""
+    """Image-space clip in pinned host memory + first annotation (H,W) uint8 on host.  raw = False: (T,3,H,W) fp32
+    ImageNet-normalised frames (what InferenceDataset hands the reference's loop); raw = True: (T,H,W,3) uint8 decoded RGB
+    (what InferenceDataset(raw=True) hands this build's loop: normalisation runs on the GPU)."""
     g = torch.Generator().manual_seed(seed)
     tr = _tracks(n_objects, g)
     colors = torch.rand(n_objects + 1, 3, generator=g).to(device)
     gd = torch.Generator(device=device).manual_seed(seed + 1)
     mean = torch.tensor(IMAGENET_MEAN, device=device).view(3, 1, 1)
     std = torch.tensor(IMAGENET_STD, device=device).view(3, 1, 1)
-    out = torch.empty((T, 3, H, W), dtype=torch.float32, pin_memory=pinned)
+    out = torch.empty((T, H, W, 3), dtype=torch.uint8, pin_memory=pinned) if raw else \
+        torch.empty((T, 3, H, W), dtype=torch.float32, pin_memory=pinned)
     for t in range(T):
         img = colors[_class_map(tr, t, H, W, device)].permute(2, 0, 1)
         img = (img + 0.05 * torch.randn(3, H, W, device=device, generator=gd)).clamp_(0, 1)
-        out[t].copy_((img - mean) / std)
+        if raw:
+            out[t].copy_((img * 255.0).round().to(torch.uint8).permute(1, 2, 0))
+        else:
+            out[t].copy_((img - mean) / std)
     return out, _class_map(tr, 0, H, W, device).to(torch.uint8).cpu()

@@ -45,3 +45,23 @@ def _worker(rank, world, port, out_dir):
 def test_two_rank_shard_and_gather(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / 'ok').read_text() == 'ok'
+
+
+def test_lpt_assignment_of_the_bench_workloads():
+    """bench.py's sharded workloads: every sequence lands on exactly one rank, the assignment is the same on every rank
+    (pure function of the costs) and its imbalance -- the scaling ceiling the bench reports -- stays small."""
+    import types
+    sys.path.insert(0, str(REPO))
+    sys.path.insert(0, str(REPO / 'semi-supervised-vos_b200'))
+    import bench
+    from vosb200.shard import assign_lpt, imbalance, sequence_cost
+    for workload, frames in (('davis30', 1999), ('ytvos', None)):
+        for world in (1, 2, 4, 8):
+            seqs = bench.workload_sequences(types.SimpleNamespace(workload=workload, clips=4, frames=70), world)
+            if frames:
+                assert sum(n for n, _ in seqs) == frames and all(34 <= n <= 104 for n, _ in seqs)
+            costs = [sequence_cost(n, 6420, 9) for n, _ in seqs]
+            a = assign_lpt(costs, world)
+            assert a == assign_lpt(costs, world)
+            assert sorted(i for r in a for i in r) == list(range(len(seqs)))
+            assert imbalance(costs, a) < 1.08
