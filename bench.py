@@ -463,16 +463,19 @@ def run_ours(args, rank, world, local_rank):
                 seg.segment(frames, first, out=outs[i], sync=False)
             torch.cuda.synchronize(dev)     # the masks of the step are in pinned host memory
 
+        def final_gather():                 # end of run: the per-sequence results of every rank -> rank 0 (NCCL send/recv)
+            res = shard.gather_results({mine[i]: outs[i].to(dev, non_blocking=True) for i in range(len(mine))}, dst=0)
+            return sum(int(v.numel()) for v in res.values())
+
         for _ in range(max(1, min(args.warmup, 2))):
             e2e_step()
+        if world > 1:
+            final_gather()                  # warm-up: NCCL sets its peer connections up on first use
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             e2e_step()
-        gathered = 0
-        if world > 1:                       # end of run: the final per-sequence result gather (NCCL), inside the timed region
-            res = shard.gather_results({mine[i]: outs[i].to(dev, non_blocking=True) for i in range(len(mine))}, dst=0)
-            gathered = sum(int(v.numel()) for v in res.values())
+        gathered = final_gather() if world > 1 else 0     # inside the timed region, once per run
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if world > 1:
