@@ -11,6 +11,7 @@ from loguru import logger
 from src.config import Config
 from src.model.vos_net import VOSNet
 from src.utils.datasets import InferenceDataset
+from src.utils.inference_utils import amp_enabled
 from src.utils.inference_utils import (inference_2_scale, inference_3_scale, inference_hor_flip,
                                        inference_multimodel, inference_single, inference_ver_flip)
 from src.utils.utils import load_model
@@ -55,6 +56,10 @@ def _load_net(arch, checkpoint):
     inference form (BatchNorm folded, bias / ReLU / residual in the convolution epilogue, fp16 as under the reference's
     autocast); VOS_FUSE_BACKBONE=0 keeps the plain module."""
     net = load_model(VOSNet(model=arch, pretrained=False), checkpoint).to(Config.DEVICE).eval()
+    if not amp_enabled():          # parity mode against the reference's fp32 CPU path: plain module, true fp32 convolutions
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        return net
     if Config.DEVICE.type == 'cuda' and arch in ('resnet18', 'resnet50', 'resnet101') and os.environ.get('VOS_FUSE_BACKBONE', '1') != '0':
         from vosb200.fused_backbone import FusedVOSNet
         return FusedVOSNet(net)

@@ -149,6 +149,14 @@ def _to_device(input):
 BACKBONE_LOOKAHEAD = 8     # frames of one video embedded per backbone call (a batch-1 ResNet is launch-bound on a B200)
 
 
+def amp_enabled() -> bool:
+    """The reference runs the network under fp16 autocast on CUDA (inference_utils.py:35,52) and so does this build.
+    VOS_AMP=0 is the parity mode against the reference's CPU (fp32) path: fp32 backbone without TF32, embeddings stored as
+    bf16 hi + lo (three tensor-core passes) -- tests/test_gpu_e2e_golden.py."""
+    import os
+    return os.environ.get('VOS_AMP', '1') != '0'
+
+
 def _embedded(models, inference_loader, total_len, disable, resize=None, shared_input=False):
     """Frame-by-frame view of the loader with the backbone run on up to BACKBONE_LOOKAHEAD consecutive frames of one
     video at a time.  Feature extraction does not depend on the propagation state (the reference calls model(input) on
@@ -171,7 +179,7 @@ def _embedded(models, inference_loader, total_len, disable, resize=None, shared_
             x, r = base, (resize[k] if isinstance(resize, (tuple, list)) else resize)
             if r is not None:
                 x = torch.nn.functional.interpolate(base, size=r(base.shape[2], base.shape[3]), mode='nearest')
-            with torch.autocast('cuda', dtype=torch.float16):
+            with torch.autocast('cuda', dtype=torch.float16, enabled=amp_enabled()):
                 feats.append(net(x))
             sizes.append((x.shape[2], x.shape[3]))
         for i, (_, video) in enumerate(pending):

@@ -1,0 +1,155 @@
+"""BASELINE.json configs[0] end to end against the REFERENCE ITSELF: one synthetic 480p clip (10 frames, 2 objects) as
+JPEGs on disk, a random-init ResNet-50 VOSNet with calibrated BatchNorm statistics (oracle/fixtures.py),
+ref_num 9, frame_range 40, sigma 8 / 21, temperature 1.  Golden = the masks the reference's own `inference_command_impl`
+wrote on the CPU in fp32, and the (d, P) predictions its predict() returned (tests/golden/e2e_480p.npz,
+oracle/make_golden_e2e.py).  Here: this build's `inference_command_impl` on the GPU from the same JPEGs and checkpoint.
+
+  * parity mode (VOS_AMP=0: fp32 backbone without TF32, embeddings as bf16 hi + lo, three tensor-core passes):
+    mask agreement >= 99.9 % over the whole clip (labels fed back for 9 frames), every differing pixel a near tie;
+    teacher-forced predictions (label history = the reference's) within 1e-3.
+  * production mode (fp16 backbone under autocast, as the reference on CUDA, one exact tensor-core pass): a random-init
+    network gives |f|^2 ~ 330 embeddings whose logits move by ~0.2 when the backbone runs in fp16, so the agreement with the
+    fp32 CPU run is REPORTED (and bounded loosely), not held to 99.9 % -- the fp16 difference is the backbone's, not the
+    propagation's: against the oracle on its own fp16 embeddings the same pipeline is exact (tests/test_gpu_cli.py)."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from oracle import fixtures as FX
+from oracle import propagation_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = np.load(str(__import__('pathlib').Path(__file__).parent / 'golden' / 'e2e_480p.npz'))
+NEAR_TIE = 2e-3
+
+
+@pytest.fixture(scope='module')
+def tree(tmp_path_factory):
+    from src.model.vos_net import VOSNet
+    root = tmp_path_factory.mktemp('e2e')
+    cfg = FX.E2E
+    frames, first = FX.e2e_frames(cfg['T'], cfg['H'], cfg['W'], cfg['n_objects'], cfg['seed'])
+    FX.e2e_write_tree(root / 'data', frames, first, cfg['video'])
+    sha = hashlib.sha256(b''.join((root / 'data/JPEGImages/480p' / cfg['video'] / f'{t:05d}.jpg').read_bytes()
+                                  for t in range(cfg['T']))).hexdigest()
+    assert sha == str(GOLDEN['jpeg_sha256']), 'the JPEG encoder of this machine does not reproduce the golden inputs'
+    torch.manual_seed(0)
+    net = VOSNet('resnet50', pretrained=False)
+    state = FX.e2e_calibrated_state(net)
+    torch.save({'state_dict': state}, root / 'ckpt.pth')
+    return root, first, state
+
+
+def _run_cli(root, save, monkeypatch, amp):
+    from src.config import Config
+    from src.inference import inference_command_impl
+    monkeypatch.setenv('VOS_AMP', '1' if amp else '0')
+    old = Config.DEVICE, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    try:
+        inference_command_impl(9, str(root / 'data'), str(root / 'ckpt.pth'), 'resnet50', 1.0, 40, 8.0, 21.0, str(save), 'cuda',
+                               'single', None, 'resnet50', False, 1.15, 'mean', disable=True)
+    finally:
+        Config.DEVICE, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    cfg = FX.E2E
+    return np.stack([np.array(Image.open(save / cfg['video'] / f'{t:05d}.png')) for t in range(1, cfg['T'])])
+
+
+def _near_tie_map():
+    """(T-1, H, W) bool: pixels whose two best reference probabilities differ by less than NEAR_TIE (at stride 8, up-sampled)."""
+    cfg = FX.E2E
+    H_d, W_d = O.lowres_dims(cfg['H'], cfg['W'])
+    top2 = np.sort(GOLDEN['preds'], 1)[:, ::-1][:, :2]
+    tie = torch.from_numpy((top2[:, 0] - top2[:, 1]) < NEAR_TIE).view(-1, H_d, W_d)
+    return torch.stack([O.upsample_mask(t.long(), H_d, W_d, cfg['H'], cfg['W']) for t in tie]).bool().numpy()
+
+
+def test_parity_mode_reproduces_the_reference_masks_from_jpegs(tree, tmp_path, monkeypatch):
+    root, first, _ = tree
+    got = _run_cli(root, tmp_path / 'out32', monkeypatch, amp=False)
+    want = GOLDEN['masks']
+    same = got == want
+    tie = _near_tie_map()
+    per_frame = [float(same[t].mean()) for t in range(len(want))]
+    print(f'parity mode (fp32 backbone, bf16x3 propagation) vs the reference from JPEGs: agreement {same.mean():.6f}, per frame '
+          f'{[round(a, 5) for a in per_frame]}, differing pixels {int((~same).sum())}, of which near ties {int((~same & tie).sum())}')
+    assert same.mean() >= 0.999
+    assert (~same & ~tie).mean() <= 2e-4      # flips away from near ties only through label feedback of earlier near-tie flips
+
+
+def test_production_mode_agreement_is_reported(tree, tmp_path, monkeypatch):
+    root, first, _ = tree
+    got = _run_cli(root, tmp_path / 'out16', monkeypatch, amp=True)
+    want = GOLDEN['masks']
+    same = got == want
+    tie = _near_tie_map()
+    print(f'production mode (fp16 backbone, one tensor-core pass) vs the fp32 reference from JPEGs: agreement {same.mean():.6f}, per frame '
+          f'{[round(float(same[t].mean()), 5) for t in range(len(want))]}, differing pixels away from near ties {float((~same & ~tie).mean()):.6f}')
+    assert same[0].mean() >= 0.95 and same.mean() >= 0.90
+
+
+@pytest.mark.parametrize('amp', [False, True])
+def test_teacher_forced_predictions_against_the_reference(tree, amp):
+    """Frame by frame with the REFERENCE's label history: prediction of this build (embeddings from its own backbone run)
+    against the reference's predict() output; max |dP| and arg-max agreement per frame."""
+    from src.model.vos_net import VOSNet
+    from vosb200 import PREC_F16, PREC_SPLIT3, PropagationEngine, normalize_frames, plan_refs
+    from vosb200.fused_backbone import FusedVOSNet
+    from vosb200.sequence import first_frame_lowres
+    root, first, state = tree
+    cfg = FX.E2E
+    H_d, W_d = O.lowres_dims(cfg['H'], cfg['W'])
+    P = H_d * W_d
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        net = VOSNet('resnet50', pretrained=False)
+        net.load_state_dict(state)
+        net = net.cuda().eval()
+        rgb = torch.stack([torch.from_numpy(np.array(Image.open(root / 'data/JPEGImages/480p' / cfg['video'] / f'{t:05d}.jpg')))
+                           for t in range(cfg['T'])]).cuda()
+        with torch.no_grad():
+            if amp:
+                feats = FusedVOSNet(net)(normalize_frames(rgb, torch.float16))
+            else:
+                feats = net(normalize_frames(rgb, torch.float32))
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    probe = torch.from_numpy(GOLDEN['probe']).long()
+    f9 = feats[9].float().reshape(256, -1)[:, probe.cuda()].cpu()
+    ref9 = torch.from_numpy(GOLDEN['feat9_probe'])
+    print(f'amp={amp}: embedding of frame 9 at 64 pixels: max |df| {float((f9 - ref9).abs().max()):.3e} (|f| max {float(ref9.abs().max()):.2f})')
+    d = cfg['n_objects'] + 1
+    eng = PropagationEngine(max_pixels=P)
+    eng.reset(H_d, W_d, cfg['H'], cfg['W'], d, PREC_F16 if amp else PREC_SPLIT3)
+    low0 = first_frame_lowres(torch.from_numpy(first), H_d, W_d)
+    # a full-resolution pixel that the reference's nearest up-sampling (inference_utils.py:74) copied from low-res row / column i
+    up_y, up_x = O.nearest_src_index(cfg['H'], H_d), O.nearest_src_index(cfg['W'], W_d)
+    ys = np.array([int(np.argmax(up_y == i)) for i in range(H_d)])
+    xs = np.array([int(np.argmax(up_x == i)) for i in range(W_d)])
+    assert (up_y[ys] == np.arange(H_d)).all() and (up_x[xs] == np.arange(W_d)).all()
+    worst, agree, n_over, n_all = 0.0, [], 0, 0
+    for t in range(cfg['T']):
+        eng.append(t, feats[t])
+        if t == 0:
+            eng.set_labels_index(0, low0.cuda())
+            continue
+        refs, sig = plan_refs(t, 40, 9, 8.0, 21.0, False)
+        got = eng.propagate(t, refs, sig, 1.0, False, write_labels=False)['prediction'].cpu()
+        want = torch.from_numpy(GOLDEN['preds'][t - 1])
+        worst = max(worst, float((got - want).abs().max()))
+        n_over += int(((got - want).abs() > 1e-3).sum())
+        n_all += got.numel()
+        agree.append(float((got.argmax(0) == want.argmax(0)).float().mean()))
+        # the reference's own labels for frame t: its full-resolution mask sampled at the nearest-neighbour source pixels
+        low = torch.from_numpy(GOLDEN['masks'][t - 1][ys][:, xs].reshape(-1).astype(np.uint8))
+        eng.set_labels_index(t, low.cuda())
+    print(f'amp={amp}: teacher-forced max |dP| {worst:.3e} ({n_over} of {n_all} probabilities off by more than 1e-3), '
+          f'arg-max agreement per frame {[round(a, 5) for a in agree]}')
+    if not amp:
+        # the embeddings themselves differ (cuDNN fp32 on the GPU against oneDNN fp32 on the CPU: accumulation order), and a
+        # random-init network's |f|^2 ~ 330 soft-max turns 1e-5 of embedding noise into ~1e-3 of probability at its sharpest
+        # pixels; the propagation's own error on IDENTICAL embeddings is 5e-5 (tests/test_gpu_parity.py)
+        assert worst <= 5e-3 and n_over <= 1e-4 * n_all and min(agree) >= 0.999
