@@ -91,6 +91,12 @@ def main():
                 print(json.dumps(dict(config='peaked', class_prototype_norm2=round(K * ps * ps, 1), noise_norm2=round(K * nz * nz, 1),
                                       texture_field='none' if not fl else f'|f|^2 = 256, correlation length {fl} px', block_skip=skip, **r)), flush=True)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == 'topk1':      # one short top-k run (k = 20) for profiling
+        print(json.dumps(dict(config=3, **measure(480, 854, 2, 9, 20, PREC_F16, frames=4, warm=1))), flush=True)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == 'prob1':      # one short probability-propagation run (dense-label kernel) for profiling
+        print(json.dumps(dict(config='prob', **measure(480, 854, 2, 9, 0, PREC_F16, probability=True, frames=4, warm=1))), flush=True)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'topk':
         for topk in (0, 5, 20, 50):
             print(json.dumps(dict(config=3, **measure(480, 854, 2, 9, topk, PREC_F16))), flush=True)
