@@ -11,7 +11,7 @@ namespace vosk {
 // maximum wins, like torch.argmax), updates the ring's label record of the target frame
 // (one-hot, or the raw prediction in probability mode -- inference_utils.py:67-71) and writes the
 // stride-8 and the nearest-upsampled full-resolution uint8 masks (inference_utils.py:74-75).
-// One block per low-resolution row so the block can emit the full-resolution rows that sample it.
+// kMergeSplit blocks per low-resolution row (column halves), each emitting the full-resolution pixels that sample its columns.
 // -------------------------------------------------------------------------------------------
 
 
@@ -27,7 +27,8 @@ __global__ void vos_decomp_tables(int32_t* __restrict__ tab, int n_pixels, int n
         tab[2 * dec.tpf + c] = static_cast<int32_t>(vosd::cta_begin(dec, c) / dec.nt);
 }
 
-constexpr int kMergeThreads = 1024;   // 128 pixel groups of 8 lanes
+constexpr int kMergeThreads = 512;    // 64 pixel groups of 8 lanes
+constexpr int kMergeSplit = 2;        // blocks per low-resolution row (column halves): 120 blocks at 480p instead of 60 on 148 SMs
 constexpr int kMergeLanes = 8;        // lanes cooperating on one target pixel
 
 template <int kCap>   // class capacity of this instantiation: kMetaClasses (the product path) or kCap
@@ -35,6 +36,7 @@ __global__ void __launch_bounds__(kMergeThreads) vos_merge_writeback(const Merge
     extern __shared__ uint8_t row_cls[];  // [w_lowres]
     pdl_launch_dependents();
     const int y = blockIdx.x;
+    const int x_lo = (prm.w_lowres * blockIdx.y) / kMergeSplit, x_hi = (prm.w_lowres * (blockIdx.y + 1)) / kMergeSplit;   // this block's columns
     const int sublane = threadIdx.x & (kMergeLanes - 1);
     const unsigned gmask = 0xffu << ((threadIdx.x & 31) & ~(kMergeLanes - 1));   // the 8 lanes of this pixel group
     const int32_t* mt0 = prm.tables + 2 * prm.tpf;
@@ -47,7 +49,7 @@ __global__ void __launch_bounds__(kMergeThreads) vos_merge_writeback(const Merge
         pdl_wait();
         waited = true;
     }
-    for (int x = threadIdx.x / kMergeLanes; x < prm.w_lowres; x += kMergeThreads / kMergeLanes) {
+    for (int x = x_lo + threadIdx.x / kMergeLanes; x < x_hi; x += kMergeThreads / kMergeLanes) {
         const int pix = y * prm.w_lowres + x;
         const int mt = pix / kTile, row = pix % kTile;
         // Everything up to here depends only on the decomposition tables.  On all but the first step of a reference count
@@ -147,7 +149,9 @@ __global__ void __launch_bounds__(kMergeThreads) vos_merge_writeback(const Merge
     const int dy0 = max(0, static_cast<int>(static_cast<float>(y) / sy) - 1);
     const int dy1 = min(prm.H, static_cast<int>(static_cast<float>(y + 1) / sy) + 2);
     for (int dx = threadIdx.x; dx < prm.W; dx += kMergeThreads) {
-        const uint8_t c = row_cls[nearest_src(dx, sx, prm.w_lowres)];
+        const int xs = nearest_src(dx, sx, prm.w_lowres);
+        if (xs < x_lo || xs >= x_hi) continue;                 // the other column half's block writes this pixel
+        const uint8_t c = row_cls[xs];
         for (int dy = dy0; dy < dy1; ++dy)
             if (nearest_src(dy, sy, prm.h_lowres) == y) prm.out_mask_fullres[static_cast<size_t>(dy) * prm.W + dx] = c;
     }

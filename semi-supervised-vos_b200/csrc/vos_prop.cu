@@ -561,7 +561,7 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     {
         TimedLaunch timed(e, VOSPROP_T_MERGE, st);
         VOS_CUDA(launch_pdl(e->d > vosk::kMetaClasses ? vosk::vos_merge_writeback<vosk::kMaxClasses> : vosk::vos_merge_writeback<vosk::kMetaClasses>,
-                            e->H_d, vosk::kMergeThreads, e->W_d, st, mp));
+                            dim3(e->H_d, vosk::kMergeSplit), vosk::kMergeThreads, e->W_d, st, mp));
     }
     VOS_CUDA(cudaGetLastError());
     if (s->write_labels) e->slot_labels[q_slot] = s->probability_propagation ? 2 : 1;
