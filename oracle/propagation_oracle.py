@@ -146,7 +146,7 @@ def predict(ref: torch.Tensor, target: torch.Tensor, ref_label: torch.Tensor,
             probability_propagation: bool, chunk: Optional[int] = None,
             topk: Optional[int] = None, return_topk_idx: bool = False,
             weights: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-            pixel_range: Optional[Tuple[int, int]] = None):
+            pixel_range: Optional[Tuple[int, int]] = None, cuda_half: bool = False):
     """Label propagation for one target frame.
 
     ref (T,K,H,W) fp32, target (K,H,W), ref_label (d,T,P) -> prediction (d,P) fp32.
@@ -164,6 +164,13 @@ def predict(ref: torch.Tensor, target: torch.Tensor, ref_label: torch.Tensor,
     restricted, per target pixel, to the k reference pixels with the largest logit (ties ->
     lowest reference index first); everything else gets weight 0.  The prior and label gather
     are unchanged, so topk >= N is exactly the reference.
+    ``cuda_half``: emulate the rounding of the reference's own CUDA path, where the embeddings leave the network in fp16
+    (autocast, inference_utils.py:52-53) and predict() runs OUTSIDE autocast on them: `ref.mm(target)` returns fp16 logits
+    (fp32 accumulate, one rounding), `*= temperature` and the softmax are fp16 (computed in fp32, rounded on output), the
+    in-place `*=` with the prior keeps fp16 (frame_idx > 15) while the out-of-place `.mul` promotes to fp32 (else branch),
+    and `.float()` precedes the label product (predict.py:49-70).  The product path of this repository keeps fp32 logits and
+    softmax on the same fp16 inputs (the more accurate of the two); tests/test_oracle_golden.py reports how far apart the
+    masks of the two are.
     """
     d = ref_label.shape[0]
     idx = torch.tensor(sample_frames(frame_idx, take_range, ref_num), dtype=torch.long)
@@ -181,6 +188,22 @@ def predict(ref: torch.Tensor, target: torch.Tensor, ref_label: torch.Tensor,
     for c0 in range(p0, p1, step):
         cs = slice(c0, min(c0 + step, p1))
         S = ref_mat.mm(tgt[:, cs])                                       # :49
+        if cuda_half:
+            S = S.half()
+            S *= temperature
+            S = S.float().softmax(dim=0).half()
+            if use_prior:
+                S = S.view(R, P, -1)
+                w_dense = weights[0][:, cs] if weights else spatial_weight((H, W), sigma_dense, cs)
+                if frame_idx > DENSE_SWITCH_FRAME:
+                    w_sparse = weights[1][:, cs] if weights else spatial_weight((H, W), sigma_sparse, cs)
+                    S[:-CONTINUOUS_FRAME] = (S[:-CONTINUOUS_FRAME].float() * w_sparse).half()
+                    S[-CONTINUOUS_FRAME:] = (S[-CONTINUOUS_FRAME:].float() * w_dense).half()
+                else:
+                    S = S.float().mul(w_dense)
+                S = S.reshape(R * P, -1)
+            out[:, cs] = lab_sel.mm(S.float())
+            continue
         S *= temperature                                                 # :52
         if topk is not None and topk < S.shape[0]:
             # stable descending sort => ties resolved toward the lowest reference index
@@ -229,7 +252,7 @@ def propagate_sequence(features: torch.Tensor, first_label_full: np.ndarray,
                        sigma_1: float = 8.0, sigma_2: float = 21.0, frame_range: int = 40,
                        ref_num: int = 9, temperature: float = 1.0,
                        probability_propagation: bool = False, chunk: Optional[int] = None,
-                       d: Optional[int] = None, topk: Optional[int] = None):
+                       d: Optional[int] = None, topk: Optional[int] = None, cuda_half: bool = False):
     """inference_single with the feature extractor factored out.
 
     features (T,K,H_d,W_d) fp32 = model(frame_t) for every frame of one video.
@@ -245,7 +268,7 @@ def propagate_sequence(features: torch.Tensor, first_label_full: np.ndarray,
     masks, preds = [], []
     for t in range(1, T):
         pred = predict(feats_history, features[t], label_history, sigma_1, sigma_2, t,
-                       frame_range, ref_num, temperature, probability_propagation, chunk, topk)
+                       frame_range, ref_num, temperature, probability_propagation, chunk, topk, cuda_half=cuda_half)
         if probability_propagation:                                      # :67-70
             new_label = pred.unsqueeze(1)
         else:

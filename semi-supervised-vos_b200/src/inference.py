@@ -99,6 +99,19 @@ def inference_command_impl(ref_num, data, resume, model, temperature, frame_rang
                                          pin_memory=True, prefetch_factor=4, persistent_workers=False)
     annotation_dir = Path(data) / 'Annotations/480p'
     last_video = sorted(v.name for v in annotation_dir.glob('*') if videos is None or v.name in videos)[0]
+    if probability_propagation:
+        # probability propagation keeps a dense label record per reference pixel: at most MAX_DENSE_CLASSES classes.  Checked for
+        # every video BEFORE anything runs, so a run does not abort half-way with earlier videos already written (the
+        # reference itself takes any d = max(label) + 1, predict.py:113)
+        import numpy as np
+        from PIL import Image
+        from vosb200._capi import MAX_DENSE_CLASSES
+        for v in sorted(annotation_dir.glob('*')):
+            if (videos is None or v.name in videos) and (v / '00000.png').is_file():
+                d = int(np.array(Image.open(v / '00000.png')).max()) + 1
+                if d > MAX_DENSE_CLASSES:
+                    raise ValueError(f'{v.name}: {d} classes in the first annotation; --probability-propagation supports at most '
+                                     f'{MAX_DENSE_CLASSES} (index-label propagation, the default, takes up to 24)')
     common = (loader, len(dataset), annotation_dir, last_video, save, sigma_1, sigma_2, frame_range, ref_num,
               temperature, probability_propagation)
     with torch.no_grad():

@@ -74,6 +74,20 @@ def required_ring_slots(frame_range: int, ref_num: int) -> int:
     return max(frame_range + CONTINUOUS_FRAME, ref_num) + 1
 
 
+def _on_device(fn):
+    """Run a method with the engine's device current: the library launches on the current CUDA device, and an engine built
+    for cuda:1 may be driven from a process whose current device is cuda:0."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        if torch.cuda.current_device() == (self.device.index or 0):
+            return fn(self, *a, **k)
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapper
+
+
 class PropagationEngine:
     def __init__(self, max_pixels: int, ring_slots: int = DEFAULT_RING_SLOTS, max_fullres_pixels: int = 0,
                  device: Optional[torch.device] = None):
@@ -112,16 +126,19 @@ class PropagationEngine:
     def launch_count(self) -> int:
         return self._lib.vosprop_launch_count(self._h)
 
+    @_on_device
     def block_skip(self, enable: bool = True):
         """Skipping of blocks whose soft-max weight is below fp32 underflow (vos_prop.h: vosprop_block_skip)."""
         capi.check(self._lib.vosprop_block_skip(self._h, int(bool(enable))))
 
+    @_on_device
     def enable_timing(self, capacity: int, classes=('append', 'affinity', 'merge')):
         """Bracket the kernel launches of the given classes with CUDA events (bench.py roofline); 0 disables."""
         mask = sum(1 << ('append', 'affinity', 'merge').index(c) for c in classes)
         capi.check(self._lib.vosprop_timing_select(self._h, mask))
         capi.check(self._lib.vosprop_timing_enable(self._h, int(capacity)))
 
+    @_on_device
     def read_timing(self):
         """{'append'|'affinity'|'merge': (total_ms, launches)} since the last read (synchronises)."""
         tot, cnt = (C.c_double * 3)(), (C.c_int64 * 3)()
@@ -129,6 +146,7 @@ class PropagationEngine:
         return {k: (tot[i], cnt[i]) for i, k in enumerate(('append', 'affinity', 'merge'))}
 
     # ------------------------------------------------------------------ per-video state
+    @_on_device
     def reset(self, H_d: int, W_d: int, H: int, W: int, d: int, precision: int = capi.PREC_SPLIT3):
         """New video.  `precision`: PREC_SPLIT3 (any embedding dtype, bf16 hi+lo, 3 tensor-core passes) or
         PREC_F16 / PREC_BF16 (embeddings already 16-bit: one exact pass); see precision_for()."""
@@ -136,6 +154,7 @@ class PropagationEngine:
         self.geom = (H_d, W_d, H, W, d)
         self.precision = int(precision)
 
+    @_on_device
     def append(self, frame_idx: int, features: torch.Tensor):
         """features: (K,H_d,W_d) or (1,K,H_d,W_d), fp32/fp16/bf16, standard or channels_last."""
         if features.dim() == 4:
@@ -157,6 +176,7 @@ class PropagationEngine:
                                                      _DTYPES[features.dtype], layout, self._stream()))
         features.record_stream(torch.cuda.current_stream(self.device))
 
+    @_on_device
     def append_frames(self, first_frame_idx: int, features: torch.Tensor, class_idx: Optional[torch.Tensor] = None):
         """features: (n,K,H_d,W_d) contiguous fp32/fp16/bf16 -> frames first_frame_idx .. +n-1; class_idx: optional
         (n,H_d,W_d) / (n,P) uint8 index labels for all of them (one call installs a labelled clip)."""
@@ -179,6 +199,7 @@ class PropagationEngine:
         if class_idx is not None:
             class_idx.record_stream(torch.cuda.current_stream(self.device))
 
+    @_on_device
     def set_labels_index(self, frame_idx: int, class_idx: torch.Tensor):
         P = self.geom[0] * self.geom[1]
         class_idx = class_idx.reshape(-1).to(device=self.device, dtype=torch.uint8).contiguous()
@@ -187,6 +208,7 @@ class PropagationEngine:
         capi.check(self._lib.vosprop_set_labels_index(self._h, frame_idx, C.c_void_p(class_idx.data_ptr()), self._stream()))
         class_idx.record_stream(torch.cuda.current_stream(self.device))
 
+    @_on_device
     def set_labels_dense(self, frame_idx: int, labels: torch.Tensor):
         P, d = self.geom[0] * self.geom[1], self.geom[4]
         labels = labels.reshape(labels.shape[0], -1).to(device=self.device, dtype=torch.float32).contiguous()
@@ -196,6 +218,7 @@ class PropagationEngine:
         labels.record_stream(torch.cuda.current_stream(self.device))
 
     # ------------------------------------------------------------------ the hot path
+    @_on_device
     def propagate(self, frame_idx: int, ref_frames: Sequence[int], ref_sigmas: Sequence[float],
                   temperature: float = 1.0, probability_propagation: bool = False, write_labels: bool = True,
                   kernel: int = capi.KERNEL_TC, want_prediction: bool = True, want_lowres: bool = True,
