@@ -69,6 +69,9 @@ def parse_args():
                     help='sequences in flight per GPU (one engine + stream each; 2 gives +2-3 %% frames/s but the lanes\' small '
                          'kernels delay the start of the other lane\'s fused kernel, so its per-launch time reads higher)')
     ap.add_argument('--no-kernel-events', action='store_true', help='do not bracket every kernel with CUDA events (roofline fields become null)')
+    ap.add_argument('--block-skip', choices=['auto', 'on', 'off'], default='auto',
+                    help='exact skipping of affinity blocks below fp32 underflow (vosprop_block_skip; auto = the engine default: it probes '
+                         '2 of every 256 launches and follows the reports -- nothing can be skipped on these low-contrast clips)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-sub-records', action='store_true', help='skip the split3 and top-k sub-records (N = 1 only)')
@@ -337,6 +340,8 @@ def run_ours(args, rank, world, local_rank):
     passes = 1 if args.precision == 'f16' else 3
     lanes = max(1, min(args.lanes, len(clips)))
     engines = [PropagationEngine(max_pixels=P, ring_slots=48, device=dev) for _ in range(lanes)]
+    for e_ in engines:
+        e_.block_skip(args.block_skip)
     lane_streams = [torch.cuda.Stream(dev) for _ in range(lanes)]
     eng = engines[0]
     masks_keep = [None] * len(clips)

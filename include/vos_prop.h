@@ -159,13 +159,18 @@ int vosprop_normalize_u8(const uint8_t* rgb, int64_t n_pixels /* n * H * W */, c
  * fills grid size and per-CTA [begin,end) of the linearised (m_tile, n_tile) space. */
 int vosprop_debug_decompose(int32_t n_pixels, int32_t n_refs, int32_t num_sms, int32_t* grid,
                             int64_t* cta_begin /* num_sms+1 entries or NULL */, int32_t* max_segments);
-/* Block skipping in the fused index-label kernel (off by default).  A 32 x 32 block of the affinity matrix whose logits all
+/* Block skipping in the fused index-label kernel: mode 0 never, 1 always, 2 auto (the default).  A 32 x 32 block of the affinity matrix whose logits all
  * lie more than 127 (log2 units) below a lower bound of the final maximum of their rows weighs less than 2^-127 of the
  * row's soft-max denominator per element -- at most ~1e-34 of a row's mass over all skipped blocks, 26 orders of magnitude
  * below fp32 resolution -- and is left out.  With peaked embeddings (|f|^2 ~ 256) about two thirds of the blocks go and
  * the launch gets 10-17 % shorter (reference tiles are then visited in a strided order that spreads the live tiles over
- * the CTAs).  It costs about 6 % when nothing can be skipped. */
-int vosprop_block_skip(vosprop_engine* e, int32_t enable);
+ * the CTAs).  It costs 6-9 % when nothing can be skipped, hence auto: a launch of the skipping kernel
+ * reports how many blocks it left out into host-mapped memory, the first launches of an engine and 2 of every 256 later
+ * ones run it as a probe, and the host switches it on at >= 5 % skipped blocks and off below 2 % -- reading the reports as
+ * they arrive, never synchronising.  Results do not depend on the mode beyond fp32 rounding (2e-6, tile order). */
+int vosprop_block_skip(vosprop_engine* e, int32_t mode);
+/* 1 if the next launch of the fused index kernel would skip (mode 1, or auto mode after a report of >= 5 % dead blocks), else 0. */
+int vosprop_block_skip_state(const vosprop_engine* e);
 /* Development aid for profiling: a bit mask that switches off parts of the fused epilogue (bit 0: all per-step
  * arithmetic, 1: label gather, 2: prior, 3: running-max update, 4: prior and packed math).  Results are WRONG
  * with any bit set; production code never calls this (flags start at 0). */

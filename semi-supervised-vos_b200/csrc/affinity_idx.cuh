@@ -673,11 +673,11 @@ __device__ __forceinline__ bool tile_exps32(RowAcc<D>& st, float (&va)[kQC], flo
         // out.  The bound is the largest running maximum any of the four column-quarter warps of this row has published in
         // shared memory (a racy, monotone-enough max: any value ever written is a true running maximum, hence a valid bound).
         // Trained embeddings (|f|^2 ~ 256) make most of the affinity matrix such blocks; low-contrast synthetic clips make
-        // none.  The test costs a shared load and a warp vote: it runs on every 16th block and, after a dead block, on each
+        // none.  The test costs a shared load and a warp vote: it runs on the 3rd, 19th, ... block of a segment and, after a dead block, on each
         // of the next 64 blocks (`probe`: bits 16.. = blocks left in that window, low bits = block counter).
         if constexpr (kSkip) {
             probe = (probe & 0xffff0000u) | ((probe + 1u) & 0xffffu);
-            if ((probe >> 16) != 0u || (probe & 15u) == 0u) {
+            if ((probe >> 16) != 0u || (probe & 15u) == 3u) {
                 const float bound = fmaxf(st.m, *rm_row);
                 // rows beyond the frame's last pixel (ragged last target tile) are discarded by the merge: they never veto
                 const bool dead = __all_sync(full, !row_real || bm - bound < -127.f);
@@ -919,6 +919,7 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
         vosd::SegIter it(dec, blockIdx.x);
         int m_tile, n0, n1;
         uint32_t buf = 0, aphase = 0;
+        int n_dead = 0;                    // kSkip: 32 x 32 blocks this warp left out (warp-uniform)
         while (it.next(m_tile, n0, n1)) {
             idx_stage_target<kSplit>(pp, prm, it.seg, m_tile, row, lane_base, sub, kIdxSub);
             RowAcc<D> st;
@@ -993,6 +994,7 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                         if (lane_is0) mbar_arrive_s(bar_empty + 8 * buf);
                         if (tile_exps32<D, kSkip>(st, va, vb, scale2, probe, rm_row, row_real))
                             tile_prior32<D>(st, va, vb, cls_lane, cls0, same32, dn, static_cast<float>(x_sub - xm), W - x_sub, pc, inv_w, w_f);
+                        else if constexpr (kSkip) ++n_dead;
                     }
                 } else {
                 int xq = x_sub;
@@ -1098,8 +1100,27 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                          (static_cast<size_t>(blockIdx.x * dec.max_segs + it.seg) * kIdxSub + sub) * kPartFloats;
             store_partial<D>(st, rec, row);
         }
+        if constexpr (kSkip) {
+            // report for the host's auto mode (vosprop_block_skip): how many blocks the launch skipped.  Warps add to the
+            // device sum; the last CTA to arrive hands the total to the host-mapped slot (the host reads it some launches
+            // later, without ever synchronising) and re-arms the scratch words for the next launch.
+            if (prm.skip_scratch != nullptr && lane == 0 && n_dead != 0) atomicAdd(prm.skip_scratch, n_dead);
+        }
     }
     idx_teardown(pp);
+    if constexpr (kSkip) {
+        if (prm.skip_scratch != nullptr && threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(prm.skip_scratch + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+                const int total = atomicExch(prm.skip_scratch, 0);
+                prm.skip_scratch[1] = 0;
+                prm.skip_report[1] = total;
+                __threadfence_system();
+                prm.skip_report[0] = prm.skip_tag;
+                __threadfence_system();
+            }
+        }
+    }
 }
 
 }  // namespace vosk

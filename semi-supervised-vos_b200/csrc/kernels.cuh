@@ -43,6 +43,7 @@ constexpr int kMetaClasses = 14;      // label floats a meta record holds (dense
 constexpr int kMaxClasses = 24;       // index-label path only: class bytes, no meta record needed (validation, d = 22)
 constexpr int kPartFloats = (2 + kMaxClasses) * kTile;  // one partial record: m, l, acc[<= 24] x 128 rows
 constexpr int kIdxSub = 4;             // vos_affinity_idx: partial records per (CTA, segment), one per 32-column quarter
+constexpr int kIdxEpiWarpsHost = 16;   // epilogue warps of vos_affinity_idx (= 32 x 32 blocks per 128 x 128 tile)
 constexpr int kQCap = 16;              // logit columns per epilogue step (a TMEM load of 16 columns)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kNegBig = -1.0e30f;  // finite "minus infinity" for the running max
@@ -74,6 +75,9 @@ struct AffinityParams {
     float* topk_bound;    // pass 1: [target tile][reference tile][4 column groups][128 rows] block maxima of logit * temperature
     const float* topk_tau;  // pass 2: [P] lower bound of each row's k-th largest logit * temperature
     int32_t tile_stride;  // 0/1, or (block skipping) the stride of the permuted tile order inside a reference frame
+    int32_t* skip_scratch;  // block skipping: device {sum of dead blocks, CTA ticket} of the launch in flight (null: no report)
+    volatile int32_t* skip_report;  // host-mapped {tag, dead blocks} slot the last CTA of the launch fills in (vosprop_block_skip auto mode)
+    int32_t skip_tag;
     int32_t tile_step;    // 0/1, or (top-k pass 1) only every tile_step-th reference tile of a target tile's row is visited
     int32_t dbg;          // development aid (vosprop_debug_flags): disables parts of the epilogue; 0 in production
     long long* dbg_clk;   // development aid: per-CTA cycle counters of the role warps' waits (null in production)

@@ -27,10 +27,10 @@ REDUCTIONS = {'maximum': lambda x, y: torch.maximum(x, y),
               'mean': lambda x, y: (x + y) / 2.0}
 
 _ENGINES = {}
-# VOS_BLOCK_SKIP=1: the fused kernel leaves out blocks of the affinity matrix whose soft-max weight is below fp32 underflow
-# (vos_prop.h: vosprop_block_skip).  10-17 % faster propagation on embeddings as peaked as trained ones, 6 % slower on
-# low-contrast ones; off unless asked for.
-_BLOCK_SKIP = os.environ.get('VOS_BLOCK_SKIP', '0') == '1'
+# VOS_BLOCK_SKIP: 0 never / 1 always / auto (default).  The fused kernel can leave out blocks of the affinity matrix whose soft-max
+# weight is below fp32 underflow (vos_prop.h: vosprop_block_skip): 6-17 % faster propagation on embeddings as peaked as trained
+# ones, 6-9 % slower where nothing can be skipped; in auto mode the engine probes and follows what its launches report.
+_BLOCK_SKIP = {'0': 'off', '1': 'on'}.get(os.environ.get('VOS_BLOCK_SKIP', 'auto'), 'auto')
 
 
 def _require_cuda() -> torch.device:

@@ -50,6 +50,7 @@ EXPORTS = {
     'vosprop_reset': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     'vosprop_append_features': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     'vosprop_block_skip': (C.c_int, [C.c_void_p, C.c_int32]),
+    'vosprop_block_skip_state': (C.c_int, [C.c_void_p]),
     'vosprop_normalize_u8': (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_int32,
                                        C.c_void_p]),
     'vosprop_append_frames': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,

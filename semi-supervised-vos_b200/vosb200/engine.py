@@ -127,9 +127,16 @@ class PropagationEngine:
         return self._lib.vosprop_launch_count(self._h)
 
     @_on_device
-    def block_skip(self, enable: bool = True):
-        """Skipping of blocks whose soft-max weight is below fp32 underflow (vos_prop.h: vosprop_block_skip)."""
-        capi.check(self._lib.vosprop_block_skip(self._h, int(bool(enable))))
+    def block_skip(self, mode='auto'):
+        """Skipping of blocks whose soft-max weight is below fp32 underflow (vos_prop.h: vosprop_block_skip):
+        False / 'off', True / 'on', or 'auto' (the engine's default: probes, then follows what the launches report)."""
+        code = {False: 0, True: 1, 'off': 0, 'on': 1, 'auto': 2, 0: 0, 1: 1, 2: 2}[mode]
+        capi.check(self._lib.vosprop_block_skip(self._h, code))
+
+    @property
+    def block_skip_active(self) -> bool:
+        """Would the next launch of the fused index kernel skip dead blocks (auto mode: what the reports so far say)?"""
+        return bool(self._lib.vosprop_block_skip_state(self._h))
 
     @_on_device
     def enable_timing(self, capacity: int, classes=('append', 'affinity', 'merge')):

@@ -215,3 +215,41 @@ def test_background_only_annotation(size):
     want_masks, want_preds = O.propagate_sequence(feats, first)
     assert preds.shape[1] == 1 and int(masks.max()) == 0 and int(want_masks.max()) == 0
     assert float((preds.cpu() - torch.stack(want_preds)).abs().max()) <= PROB_ATOL
+
+
+def test_block_skipping_auto_mode_follows_the_data_and_never_changes_the_numbers():
+    """vosprop_block_skip auto mode (the engine default): the first launches probe; embeddings as peaked as a trained
+    network's (|f|^2 = 256, texture-like) switch the skipping kernel on, the low-contrast clips of the bench do not.  In auto
+    mode the skipping kernel keeps the natural tile order, so it adds the same numbers in the same order as the plain kernel
+    minus exact zeros: the predictions of an 'auto' and an 'off' engine are equal whichever kernel ran."""
+    from vosb200 import PREC_F16, plan_refs
+    dev = torch.device('cuda')
+    K, H, W, T = 256, 480, 856, 12
+    H_d, W_d = H // 8, W // 8
+    P = H_d * W_d
+    g = torch.Generator(device=dev).manual_seed(11)
+    ys, xs = torch.meshgrid(torch.arange(H_d, device=dev, dtype=torch.float32), torch.arange(W_d, device=dev, dtype=torch.float32), indexing='ij')
+    pos = torch.stack([ys.reshape(-1), xs.reshape(-1)], 1)
+    field = torch.cos(pos @ (torch.randn(2, K, device=dev, generator=g) / 4.0) + torch.rand(K, device=dev, generator=g) * 6.2831853) * (2.0 / K) ** 0.5 * 16.0
+    cls = (torch.rand(T, P, device=dev, generator=g) < 0.3).to(torch.uint8)
+    for name, base in (('peaked', field), ('flat', torch.zeros_like(field))):
+        feats = [(base + 0.3 * torch.randn(P, K, device=dev, generator=g)).t().reshape(K, H_d, W_d).half().contiguous() for _ in range(T)]
+        engines = {}
+        for mode in ('auto', 'off'):
+            e = _engine(P)
+            e.block_skip(mode)
+            e.reset(H_d, W_d, H, W, 2, PREC_F16)
+            for f in range(T):
+                e.append(f, feats[f])
+                e.set_labels_index(f, cls[f])
+            engines[mode] = e
+        active = []
+        for t in range(1, T):
+            refs, sig = plan_refs(t, 40, 9, 8.0, 21.0, False)
+            a = engines['auto'].propagate(t, refs, sig, 1.0, False, write_labels=False)['prediction']
+            b = engines['off'].propagate(t, refs, sig, 1.0, False, write_labels=False)['prediction']
+            torch.cuda.synchronize()                       # the report of this launch is in host memory now
+            active.append(engines['auto'].block_skip_active)
+            assert float((a - b).abs().max()) <= 1e-7, (name, t)
+        print(f'{name}: skipping active after each step: {[int(x) for x in active]}')
+        assert active[-1] == (name == 'peaked') and not engines['off'].block_skip_active

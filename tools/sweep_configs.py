@@ -31,7 +31,7 @@ def measure(H, W, n_obj, ref_num, topk, prec, frames=8, t0=46, probability=False
     proto = torch.randn(n_obj + 1, K, device=dev, generator=g) * proto_scale
     eng = PropagationEngine(max_pixels=P, ring_slots=max(48, ref_num + 2), device=dev)
     eng.reset(H_d, W_d, H, W, n_obj + 1, prec)
-    eng.block_skip(block_skip)
+    eng.block_skip('on' if block_skip is True else ('off' if block_skip is False else block_skip))
     cm = synthetic._class_map(synthetic._tracks(n_obj, torch.Generator().manual_seed(2)), 0, H_d, W_d, dev).reshape(-1)
     feat_dtype = torch.float16 if prec == PREC_F16 else torch.float32
 
@@ -86,7 +86,7 @@ def main():
         # embedding norm of trained features (|f|^2 ~ 256) instead of the low-contrast bench clips (|f|^2 ~ 26): blocks of the
         # affinity matrix that underflow to exactly zero are skipped by the fused kernel
         for ps, nz, fl in ((0.3, 0.1, 0.0), (0.95, 0.3, 0.0), (0.3, 0.1, 12.0), (0.3, 0.1, 6.0), (0.3, 0.1, 3.0)):
-            for skip in (False, True):
+            for skip in (False, True, 'auto'):
                 r = measure(480, 854, 2, 9, 0, PREC_F16, proto_scale=ps, noise=nz, block_skip=skip, field_len=fl)
                 print(json.dumps(dict(config='peaked', class_prototype_norm2=round(K * ps * ps, 1), noise_norm2=round(K * nz * nz, 1),
                                       texture_field='none' if not fl else f'|f|^2 = 256, correlation length {fl} px', block_skip=skip, **r)), flush=True)
