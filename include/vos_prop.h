@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define VOSPROP_ABI_VERSION 3
+#define VOSPROP_ABI_VERSION 4
 #define VOSPROP_MAX_REFS 32     /* reference frames per step (reference default ref_num = 9)   */
 #define VOSPROP_MAX_CLASSES 24  /* d = objects + 1; 15..24 (validation: 22 annotation centroids, src/train.py:206) run with index
                                    labels only: no dense labels, no probability propagation, no top-k, W_d >= 32   */

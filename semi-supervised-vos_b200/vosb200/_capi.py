@@ -14,7 +14,7 @@ F32, F16, BF16 = 0, 1, 2
 NCHW, NHWC = 0, 1
 KERNEL_TC, KERNEL_SIMT, KERNEL_TC_DENSE = 0, 1, 2
 PREC_SPLIT3, PREC_F16, PREC_BF16 = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE = 0, -1, -2, -3, -4
 
 # VOS_LIB_NAME selects a variant build of the same sources (vosb200/build.py); the product is libvosprop.so

@@ -30,7 +30,7 @@ def test_exports_every_declared_symbol(lib):
     assert declared == set(_capi.EXPORTS), declared ^ set(_capi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.vosprop_abi_version() == 3
+    assert lib.vosprop_abi_version() == 4
 
 
 def test_struct_layout_matches_header(lib):
