@@ -16,10 +16,10 @@ cudaError_t launch_affinity_idx(int D, bool split, bool wide, bool skip, int gri
     }
 }
 
-cudaError_t launch_affinity_dense(int D, bool simt, int grid, cudaStream_t st, const CUtensorMap& tmap_hi, const CUtensorMap& tmap_lo,
+cudaError_t launch_affinity_dense(int D, int which, int grid, cudaStream_t st, const CUtensorMap& tmap_hi, const CUtensorMap& tmap_lo,
                                   const AffinityParams& prm) {
     switch (D) {
-#define VOS_CASE(d) case d: return launch_dense_d<d>(simt, grid, st, tmap_hi, tmap_lo, prm);
+#define VOS_CASE(d) case d: return launch_dense_d<d>(which, grid, st, tmap_hi, tmap_lo, prm);
         VOS_FOR_EACH_D(VOS_CASE)
 #undef VOS_CASE
         default: return cudaErrorInvalidValue;

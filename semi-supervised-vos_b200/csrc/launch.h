@@ -29,14 +29,15 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 // vos_affinity_idx<D, split, wide, skip>; D in {2, 3, 4, 6, 8, 11, 14, 24} (24: wide instantiation only)
 cudaError_t launch_affinity_idx(int D, bool split, bool wide, bool skip, int grid, cudaStream_t st, const CUtensorMap& tmap_hi,
                                 const CUtensorMap& tmap_lo, const AffinityParams& prm);
-// vos_affinity_tc<D> (dense label records) / vos_affinity_simt<D> (fp32 checker); D in {2, 3, 4, 6, 8, 11, 14}
-cudaError_t launch_affinity_dense(int D, bool simt, int grid, cudaStream_t st, const CUtensorMap& tmap_hi, const CUtensorMap& tmap_lo,
+// which = 0: vos_affinity_tc<D> (dense label records), 1: vos_affinity_simt<D> (fp32 checker), 2: vos_affinity_prob<D> (dense labels,
+// no prior); D in {2, 3, 4, 6, 8, 11, 14}
+cudaError_t launch_affinity_dense(int D, int which, int grid, cudaStream_t st, const CUtensorMap& tmap_hi, const CUtensorMap& tmap_lo,
                                   const AffinityParams& prm);
 
 // per-D pieces (one translation unit each)
 template <int D> cudaError_t launch_idx_d(bool split, bool wide, bool skip, int grid, cudaStream_t st, const CUtensorMap& tmap_hi,
                                           const CUtensorMap& tmap_lo, const AffinityParams& prm);
-template <int D> cudaError_t launch_dense_d(bool simt, int grid, cudaStream_t st, const CUtensorMap& tmap_hi, const CUtensorMap& tmap_lo,
+template <int D> cudaError_t launch_dense_d(int which, int grid, cudaStream_t st, const CUtensorMap& tmap_hi, const CUtensorMap& tmap_lo,
                                             const AffinityParams& prm);
 
 }  // namespace vosk

@@ -80,6 +80,7 @@ struct vosprop_engine {
     int32_t* skip_scratch = nullptr;          // device {sum, ticket}
     volatile int32_t* skip_report = nullptr;  // host-mapped [kSkipSlots][2] = {tag, dead blocks}
     int32_t* skip_report_dev = nullptr;
+    int last_dense_kernel = -1;       // 0 vos_affinity_tc, 1 simt checker, 2 vos_affinity_prob
     int skip_on = 0;                  // auto: current decision
     int64_t skip_launch = 0;          // launches of the fused index kernel so far
     int64_t skip_probe_until = 0;     // launches < this run the skipping kernel to probe
@@ -200,7 +201,13 @@ int dispatch_affinity(vosprop_engine* e, const vosk::AffinityParams& prm, int gr
         }
         ce = vosk::launch_affinity_idx(D, split, wide, skip, grid, st, e->tmap_hi, e->tmap_lo, prm_k);
     } else {
-        ce = vosk::launch_affinity_dense(D, kernel == VOSPROP_KERNEL_SIMT, grid, st, e->tmap_hi, e->tmap_lo, prm);
+        // dense label records: without any prior (probability propagation, predict.py:58) the TMEM-A kernel with 16 epilogue
+        // warps; with a prior (float label histories of the stateless predict() adapter) or on request the round-1 kernel
+        bool no_prior = true;
+        for (int r = 0; r < prm.n_refs; ++r) no_prior = no_prior && prm.ref_coef[r] == 0.f;
+        const int which = kernel == VOSPROP_KERNEL_SIMT ? 1 : (no_prior ? 2 : 0);
+        e->last_dense_kernel = which;
+        ce = vosk::launch_affinity_dense(D, which, grid, st, e->tmap_hi, e->tmap_lo, prm);
     }
     if (ce != cudaSuccess) return fail(VOSPROP_ERR_CUDA, "affinity kernel launch failed: %s", cudaGetErrorString(ce));
     VOS_CUDA(cudaGetLastError());
@@ -603,7 +610,7 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     mp.n_pixels = e->P; mp.p_pad = e->p_pad; mp.w_lowres = e->W_d; mp.h_lowres = e->H_d; mp.n_refs = s->n_refs;
     mp.num_sms = e->num_sms; mp.d = e->d; mp.H = e->H; mp.W = e->W; mp.q_slot = q_slot;
     mp.write_labels = s->write_labels; mp.probability = s->probability_propagation;
-    mp.n_sub = (kernel == VOSPROP_KERNEL_TC) ? vosk::kIdxSub : 2;
+    mp.n_sub = (kernel == VOSPROP_KERNEL_TC || e->last_dense_kernel == 2) ? vosk::kIdxSub : 2;
     {   // which CTAs hold partials of which target tile: computed once per reference count and video (tiny kernel,
         // stream-ordered, so a host that runs clips ahead of the device never races with it)
         int32_t* dev = e->tables + static_cast<size_t>(s->n_refs) * e->table_stride;

@@ -17,7 +17,7 @@ from pathlib import Path
 CSRC = Path(__file__).resolve().parent.parent / 'csrc'
 LIB = CSRC / 'libvosprop.so'
 CLASS_CAPS = (2, 3, 4, 6, 8, 11, 14)
-HEADERS = ['kernels.cuh', 'side_kernels.cuh', 'affinity_idx.cuh', 'affinity_topk.cuh', 'topk_params.h', 'launch.h', 'ptx.cuh',
+HEADERS = ['kernels.cuh', 'side_kernels.cuh', 'affinity_idx.cuh', 'affinity_topk.cuh', 'affinity_prob.cuh', 'topk_params.h', 'launch.h', 'ptx.cuh',
            'decompose.h', '../../include/vos_prop.h']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC']
 
