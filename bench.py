@@ -386,6 +386,7 @@ def run_ours(args, rank, world, local_rank):
 
     my_frames = sum(seqs[i][0] - 1 for i in mine)
     ms_local, (aff_ms, aff_n), clock_summary, gpu_launches = timed_steps(prop_step, args.warmup, args.steps, len(clips), my_frames)
+    skip_active_main = bool(eng.block_skip_active)
     stage = {'append': (0.0, 0), 'merge': (0.0, 0)}
     if not args.no_kernel_events and clips:
         eng.enable_timing(4 * seqs[mine[0]][0] + 16, classes=('append', 'merge'))
@@ -437,6 +438,7 @@ def run_ours(args, rank, world, local_rank):
         ms_, (a_ms, a_n), _, _ = timed_steps(lambda: prop_step(fp32_clips, s_objs, s_keep), 1, 2, len(sample), sample_frames_n)
         flops_ = sum(clip_flops(seqs[i][0], P) for i in sample) * 2
         sub['split3'] = {'value': sample_frames_n / (ms_ / 1e3), 'unit': UNIT, 'dtype': 'bf16x3', 'sample': sample_txt,
+                         'block_skip_active': bool(eng.block_skip_active),
                          'precision': 'fp32 embeddings stored as bf16 hi + lo, three tcgen05 passes per logit (max |dP| 5e-5 against the fp32 reference)',
                          'roofline': roofline_of(a_ms, a_n, flops_, 3, 'split3', 'vos_affinity_idx<split>')}
         del fp32_clips
@@ -502,6 +504,7 @@ def run_ours(args, rank, world, local_rank):
                 'dtype': 'f16' if args.precision == 'f16' else 'bf16x3', 'data': 'synthetic',
                 'config': workload_config(args, world, seqs, assignment, imbalance),
                 'clocks': clock_summary, 'e2e': e2e, 'gpu_launches': int(gpu_launches),
+                'block_skip': {'mode': args.block_skip, 'active_after_timed_region': skip_active_main},
                 'roofline': roofline, 'side_kernels': side, 'cpu_baseline': cpu}
         line.update(sub)
         print(json.dumps(line), flush=True)
