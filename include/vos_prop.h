@@ -114,11 +114,15 @@ int vosprop_reset(vosprop_engine* e, int32_t H_d, int32_t W_d, int32_t H, int32_
 int vosprop_append_features(vosprop_engine* e, int32_t frame_idx, const void* features,
                             int32_t dtype, int32_t layout, void* stream);
 
-/* Append `n_frames` consecutive frames first_frame_idx .. +n_frames-1 in one call: `features` holds n_frames maps
- * back to back (each K x P or P x K elements of `dtype`); when `class_idx` is not NULL it holds n_frames x P class
- * bytes and every appended frame also gets its index labels.  Same effect as n_frames x (vosprop_append_features
- * [+ vosprop_set_labels_index]); it exists for callers that install a whole labelled clip at once -- the reference
- * frames of a validation clip (src/train.py:181-207: ref = features[:, 0:num_frames-1] with their annotations). */
+/* Append `n_frames` consecutive frames first_frame_idx .. +n_frames-1 in ONE kernel launch: `features` holds n_frames
+ * maps back to back (each K x P or P x K elements of `dtype`); frame first_frame_idx + i goes to ring slot
+ * (first_frame_idx + i) % ring_slots.  When `class_idx` is not NULL it holds n_frames x P class bytes and every appended
+ * frame also gets its index labels.  Same effect as n_frames x (vosprop_append_features [+ vosprop_set_labels_index]).
+ * Two callers: a whole labelled clip installed at once -- the reference frames of a validation clip (src/train.py:181-207:
+ * ref = features[:, 0:num_frames-1] with their annotations) -- and the inference loop, which appends the frames of a
+ * backbone batch AHEAD of the frame being propagated (a ring of 45 + n slots keeps every frame sample_frames can still
+ * pick, predict.py:74-89): one 3.3 MB copy per frame is launch-latency-bound (6-8 us at 0.8 TB/s), 19 frames in one
+ * launch run at 2.9 TB/s and leave the per-frame chain affinity -> merge -> affinity. */
 int vosprop_append_frames(vosprop_engine* e, int32_t first_frame_idx, int32_t n_frames, const void* features,
                           int32_t dtype, int32_t layout, const uint8_t* class_idx, void* stream);
 

@@ -54,7 +54,10 @@ constexpr int kIdxSmem = kIdxRingChunks * kChunkBytes + 512 + kIdxRowMaxBytes + 
 template <bool kSplit>
 struct IdxCfg {
     static constexpr int kChunks = kSplit ? 2 * kNKC : kNKC;   // smem chunks per reference tile
-    static constexpr int kAccBufs = kSplit ? 2 : 3;
+#ifndef VOS_ACC_BUFS
+#define VOS_ACC_BUFS 3               // experiment hook: -DVOS_ACC_BUFS=2 measures what one accumulator less costs (profiles/README.md)
+#endif
+    static constexpr int kAccBufs = kSplit ? 2 : VOS_ACC_BUFS;
     static constexpr uint32_t kTmemQ = kAccBufs * kTile;       // first TMEM column of the target tile
     static constexpr int kQChunks = kSplit ? 8 : 4;            // 32-column TMEM chunks of the target tile
     static constexpr int kGroup = kSplit ? 2 : 4;              // chunks per pipeline stage: a hi+lo pair / a whole tile
@@ -888,7 +891,7 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
     extern __shared__ uint8_t smem_raw[];
     pdl_launch_dependents();
     const IdxPipe pp = idx_setup<Cfg::kGroup, Cfg::kStages>(smem_raw, &tmap_hi, &tmap_lo, Cfg::kAccBufs, kIdxEpiWarps);
-    pdl_wait();       // barriers, TMEM and tensor-map prefetch are set up while the append kernel before us drains
+    pdl_wait();       // barriers, TMEM and tensor-map prefetch are set up while the kernel before us drains
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const vosd::Decomp dec = vosd::make_decomp(prm.n_pixels, prm.n_refs, prm.num_sms);
@@ -915,7 +918,10 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
         const float inv_w = prm.inv_w, scale2 = prm.scale2;
         const int x_step = kTile % W;
         const int last_valid = prm.n_pixels - (dec.tpf - 1) * kTile - sub * 32;   // real columns of this warp in a frame's last tile
-        const uint32_t ragged = last_valid >= 32 ? 0xffffffffu : (last_valid <= 0 ? 0u : ((1u << last_valid) - 1u));
+        const uint32_t ragged = pin_reg(last_valid >= 32 ? 0xffffffffu : (last_valid <= 0 ? 0u : ((1u << last_valid) - 1u)));
+        // tile index (inside a frame) from which this warp's columns are ragged: the last tile, or none at all
+        const int ragged_tile = pin_reg(ragged == 0xffffffffu ? dec.tpf : dec.tpf - 1);
+        const uint32_t sub_lane = pin_reg(static_cast<uint32_t>(sub * 32 + lane));
         vosd::SegIter it(dec, blockIdx.x);
         int m_tile, n0, n1;
         uint32_t buf = 0, aphase = 0;
@@ -959,7 +965,7 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                 const uint32_t cls_lane = cls_next;
                 {   // prefetch the next tile's class bytes: the load's latency hides behind this tile's arithmetic
                     const bool wrap_ref = j + 1 == dec.tpf;
-                    const uint8_t* nxt = wrap_ref ? prm.cls + static_cast<size_t>(prm.ref_slot[min(r + 1, prm.n_refs - 1)]) * prm.p_pad + sub * 32 + lane
+                    const uint8_t* nxt = wrap_ref ? prm.cls + static_cast<size_t>(prm.ref_slot[min(r + 1, prm.n_refs - 1)]) * prm.p_pad + sub_lane
                                                   : cls_p + kTile;
                     if constexpr (kSkip) {
                         if (!wrap_ref) {
@@ -969,13 +975,14 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                     }
                     if (nt + 1 < n1) cls_next = __ldg(nxt);
                 }
-                const uint32_t valid32 = (jp == dec.tpf - 1) ? ragged : full;
+                const bool all_valid = jp < ragged_tile;               // every column of this warp is a real pixel
+                const uint32_t valid32 = all_valid ? full : ragged;
                 mbar_wait_hint_s(bar_full + 8 * buf, aphase, 20000u);
                 tc_fence_after_sync();
                 const uint32_t taddr = tbase + buf * kTile;
                 const uint32_t cls0 = __shfl_sync(full, cls_lane, 0);
                 const uint32_t same32 = __ballot_sync(full, cls_lane == cls0);
-                if (valid32 == full && (kWide || pc.chain_always) && !VOS_DBG_ANY(prm)) {
+                if (all_valid && (kWide || pc.chain_always) && !VOS_DBG_ANY(prm)) {
                     float va[kQC], vb[kQC];
                     if constexpr (kWide) {
                         tmem_ld_32x32b_x16(taddr, va);
@@ -1075,7 +1082,7 @@ vos_affinity_idx(const __grid_constant__ CUtensorMap tmap_hi, const __grid_const
                     dn = sub * 32 - m;
                     if (nt + 1 < n1) {
                         pc = prior_const(prm.ref_coef[r], inv_w, w_f, h_f);
-                        cls_p = prm.cls + static_cast<size_t>(prm.ref_slot[r]) * prm.p_pad + sub * 32 + lane;
+                        cls_p = prm.cls + static_cast<size_t>(prm.ref_slot[r]) * prm.p_pad + sub_lane;
                     }
                 } else if constexpr (kSkip) {
                     int step = prm.tile_stride;               // tiles forward; minus a whole frame when the index wraps

@@ -184,13 +184,25 @@ __device__ __forceinline__ uint32_t pack_hi(float x0, float x1, int fmt, uint32_
     return reinterpret_cast<const uint32_t&>(h);
 }
 
+// A launch appends a batch of consecutive frames (grid z / y = frame of the batch): frame first_frame + i goes to ring slot
+// (first_frame + i) % ring_slots.  One launch per batch instead of one per frame takes the append off the per-frame chain
+// affinity -> merge -> affinity (a 3.3 MB copy alone is launch-latency-bound: 6-8 us at 0.8 TB/s).
+struct AppendSlots {
+    int32_t first_frame, ring_slots, p_pad;
+    __device__ __forceinline__ size_t row0(unsigned i) const {
+        return static_cast<size_t>((first_frame + static_cast<int>(i)) % ring_slots) * p_pad;
+    }
+};
+
 // Channel-major source (torch default): 32 pixels x 64 channels per block, transposed through shared memory.
 template <typename T>
 __global__ void __launch_bounds__(256) vos_append_nchw(const T* __restrict__ src, __nv_bfloat16* __restrict__ hi,
-                                                       __nv_bfloat16* __restrict__ lo, int n_pixels, size_t slot_row0, int fmt) {
+                                                       __nv_bfloat16* __restrict__ lo, int n_pixels, AppendSlots sl, int fmt) {
     __shared__ float tile[64][33];
     pdl_launch_dependents();
     pdl_wait();                           // the ring slot being overwritten is no longer read by earlier kernels
+    const size_t slot_row0 = sl.row0(blockIdx.z);
+    src += static_cast<size_t>(blockIdx.z) * kK * n_pixels;      // frame blockIdx.z of the batch
     const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 64;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int p = p0 + lane;
@@ -218,11 +230,13 @@ __global__ void __launch_bounds__(256) vos_append_nchw(const T* __restrict__ src
 // Requires a 16-byte aligned source (the host falls back to the pair kernel otherwise).
 template <typename T>
 __global__ void __launch_bounds__(256) vos_append_nhwc8(const T* __restrict__ src, __nv_bfloat16* __restrict__ hi,
-                                                        __nv_bfloat16* __restrict__ lo, int n_pixels, size_t slot_row0, int fmt) {
+                                                        __nv_bfloat16* __restrict__ lo, int n_pixels, AppendSlots sl, int fmt) {
     pdl_launch_dependents();
     pdl_wait();
     const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;  // group of 8 channels
     if (i >= static_cast<size_t>(n_pixels) * (kK / 8)) return;
+    const size_t slot_row0 = sl.row0(blockIdx.y);
+    src += static_cast<size_t>(blockIdx.y) * kK * n_pixels;      // frame blockIdx.y of the batch
     float x[8];
     if (sizeof(T) == 4) {
         const float4 a = reinterpret_cast<const float4*>(src)[2 * i], b = reinterpret_cast<const float4*>(src)[2 * i + 1];
@@ -245,11 +259,13 @@ __global__ void __launch_bounds__(256) vos_append_nhwc8(const T* __restrict__ sr
 
 template <typename T>
 __global__ void __launch_bounds__(256) vos_append_nhwc(const T* __restrict__ src, __nv_bfloat16* __restrict__ hi,
-                                                       __nv_bfloat16* __restrict__ lo, int n_pixels, size_t slot_row0, int fmt) {
+                                                       __nv_bfloat16* __restrict__ lo, int n_pixels, AppendSlots sl, int fmt) {
     pdl_launch_dependents();
     pdl_wait();
     const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;  // channel pair index
     if (i >= static_cast<size_t>(n_pixels) * (kK / 2)) return;
+    const size_t slot_row0 = sl.row0(blockIdx.y);
+    src += static_cast<size_t>(blockIdx.y) * kK * n_pixels;
     uint32_t lo_bits = 0;
     const size_t off = slot_row0 * (kK / 2) + i;
     reinterpret_cast<uint32_t*>(hi)[off] = pack_hi(to_f32<T>(src[2 * i]), to_f32<T>(src[2 * i + 1]), fmt, lo_bits);

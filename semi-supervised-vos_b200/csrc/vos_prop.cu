@@ -258,9 +258,7 @@ int propagate_topk(vosprop_engine* e, const vosprop_step* s, vosk::AffinityParam
     if (bound_floats > e->topk_bound_floats) {
         if (e->topk_bound) {
             VOS_CUDA(cudaStreamSynchronize(st));          // a scan of an earlier step may still be writing the old buffer
-            cudaFree(e->skip_scratch);
-    if (e->skip_report) cudaFreeHost(const_cast<int32_t*>(e->skip_report));
-    cudaFree(e->topk_bound);
+            cudaFree(e->topk_bound);
             e->topk_bound = nullptr;
             e->topk_bound_floats = 0;
         }
@@ -447,46 +445,56 @@ int vosprop_reset(vosprop_engine* e, int32_t H_d, int32_t W_d, int32_t H, int32_
     return VOSPROP_OK;
 }
 
-int vosprop_append_features(vosprop_engine* e, int32_t frame_idx, const void* features, int32_t dtype,
-                            int32_t layout, void* stream) {
-    int rc = check_frame(e, frame_idx);
+// One launch appends n consecutive frames (side_kernels.cuh: AppendSlots); the source holds them back to back.
+static int append_batch(vosprop_engine* e, int32_t first_frame, int32_t n, const void* features, int32_t dtype, int32_t layout,
+                        cudaStream_t st) {
+    int rc = check_frame(e, first_frame);
     if (rc) return rc;
     if (!features) return fail(VOSPROP_ERR_INVALID, "null features");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int slot = frame_idx % e->cfg.ring_slots;
-    const size_t row0 = static_cast<size_t>(slot) * e->p_pad;
+    if (n < 1 || n > e->cfg.ring_slots) return fail(VOSPROP_ERR_INVALID, "n_frames=%d outside 1..ring_slots=%d", n, e->cfg.ring_slots);
     const int P = e->P;
     if (dtype != VOSPROP_F32 && dtype != VOSPROP_F16 && dtype != VOSPROP_BF16) return fail(VOSPROP_ERR_INVALID, "unknown dtype %d", dtype);
     if ((e->precision == VOSPROP_PREC_F16 && dtype != VOSPROP_F16) || (e->precision == VOSPROP_PREC_BF16 && dtype != VOSPROP_BF16))
         return fail(VOSPROP_ERR_INVALID, "this video was reset in %s precision: embeddings must arrive in that dtype (got dtype %d); "
                     "use VOSPROP_PREC_SPLIT3 for fp32 embeddings", e->precision == VOSPROP_PREC_F16 ? "F16" : "BF16", dtype);
     const int fmt = e->precision;   // enum values coincide with vosk::kFmt*
+    const vosk::AppendSlots sl{first_frame, e->cfg.ring_slots, e->p_pad};
+    const unsigned nf = static_cast<unsigned>(n);
     TimedLaunch timed(e, VOSPROP_T_APPEND, st);
     if (layout == VOSPROP_NCHW) {
-        const dim3 grid((P + 31) / 32, vosk::kK / 64);
-        if (dtype == VOSPROP_F32) VOS_CUDA(launch_pdl(vosk::vos_append_nchw<float>, grid, 256, 0, st, static_cast<const float*>(features), e->ring_hi, e->ring_lo, P, row0, fmt));
-        else if (dtype == VOSPROP_F16) VOS_CUDA(launch_pdl(vosk::vos_append_nchw<__half>, grid, 256, 0, st, static_cast<const __half*>(features), e->ring_hi, e->ring_lo, P, row0, fmt));
-        else VOS_CUDA(launch_pdl(vosk::vos_append_nchw<__nv_bfloat16>, grid, 256, 0, st, static_cast<const __nv_bfloat16*>(features), e->ring_hi, e->ring_lo, P, row0, fmt));
+        const dim3 grid((P + 31) / 32, vosk::kK / 64, nf);
+        if (dtype == VOSPROP_F32) VOS_CUDA(launch_pdl(vosk::vos_append_nchw<float>, grid, 256, 0, st, static_cast<const float*>(features), e->ring_hi, e->ring_lo, P, sl, fmt));
+        else if (dtype == VOSPROP_F16) VOS_CUDA(launch_pdl(vosk::vos_append_nchw<__half>, grid, 256, 0, st, static_cast<const __half*>(features), e->ring_hi, e->ring_lo, P, sl, fmt));
+        else VOS_CUDA(launch_pdl(vosk::vos_append_nchw<__nv_bfloat16>, grid, 256, 0, st, static_cast<const __nv_bfloat16*>(features), e->ring_hi, e->ring_lo, P, sl, fmt));
     } else if (layout == VOSPROP_NHWC) {
-        if (reinterpret_cast<uintptr_t>(features) % 16 == 0) {
-            const unsigned grid = static_cast<unsigned>((static_cast<size_t>(P) * (vosk::kK / 8) + 255) / 256);
-            if (dtype == VOSPROP_F32) VOS_CUDA(launch_pdl(vosk::vos_append_nhwc8<float>, grid, 256, 0, st, static_cast<const float*>(features), e->ring_hi, e->ring_lo, P, row0, fmt));
-            else if (dtype == VOSPROP_F16) VOS_CUDA(launch_pdl(vosk::vos_append_nhwc8<__half>, grid, 256, 0, st, static_cast<const __half*>(features), e->ring_hi, e->ring_lo, P, row0, fmt));
-            else VOS_CUDA(launch_pdl(vosk::vos_append_nhwc8<__nv_bfloat16>, grid, 256, 0, st, static_cast<const __nv_bfloat16*>(features), e->ring_hi, e->ring_lo, P, row0, fmt));
+        const size_t frame_bytes = static_cast<size_t>(vosk::kK) * P * (dtype == VOSPROP_F32 ? 4 : 2);
+        if (reinterpret_cast<uintptr_t>(features) % 16 == 0 && (n == 1 || frame_bytes % 16 == 0)) {
+            const dim3 grid(static_cast<unsigned>((static_cast<size_t>(P) * (vosk::kK / 8) + 255) / 256), nf);
+            if (dtype == VOSPROP_F32) VOS_CUDA(launch_pdl(vosk::vos_append_nhwc8<float>, grid, 256, 0, st, static_cast<const float*>(features), e->ring_hi, e->ring_lo, P, sl, fmt));
+            else if (dtype == VOSPROP_F16) VOS_CUDA(launch_pdl(vosk::vos_append_nhwc8<__half>, grid, 256, 0, st, static_cast<const __half*>(features), e->ring_hi, e->ring_lo, P, sl, fmt));
+            else VOS_CUDA(launch_pdl(vosk::vos_append_nhwc8<__nv_bfloat16>, grid, 256, 0, st, static_cast<const __nv_bfloat16*>(features), e->ring_hi, e->ring_lo, P, sl, fmt));
         } else {
-            const unsigned grid = static_cast<unsigned>((static_cast<size_t>(P) * (vosk::kK / 2) + 255) / 256);
-            if (dtype == VOSPROP_F32) VOS_CUDA(launch_pdl(vosk::vos_append_nhwc<float>, grid, 256, 0, st, static_cast<const float*>(features), e->ring_hi, e->ring_lo, P, row0, fmt));
-            else if (dtype == VOSPROP_F16) VOS_CUDA(launch_pdl(vosk::vos_append_nhwc<__half>, grid, 256, 0, st, static_cast<const __half*>(features), e->ring_hi, e->ring_lo, P, row0, fmt));
-            else VOS_CUDA(launch_pdl(vosk::vos_append_nhwc<__nv_bfloat16>, grid, 256, 0, st, static_cast<const __nv_bfloat16*>(features), e->ring_hi, e->ring_lo, P, row0, fmt));
+            const dim3 grid(static_cast<unsigned>((static_cast<size_t>(P) * (vosk::kK / 2) + 255) / 256), nf);
+            if (dtype == VOSPROP_F32) VOS_CUDA(launch_pdl(vosk::vos_append_nhwc<float>, grid, 256, 0, st, static_cast<const float*>(features), e->ring_hi, e->ring_lo, P, sl, fmt));
+            else if (dtype == VOSPROP_F16) VOS_CUDA(launch_pdl(vosk::vos_append_nhwc<__half>, grid, 256, 0, st, static_cast<const __half*>(features), e->ring_hi, e->ring_lo, P, sl, fmt));
+            else VOS_CUDA(launch_pdl(vosk::vos_append_nhwc<__nv_bfloat16>, grid, 256, 0, st, static_cast<const __nv_bfloat16*>(features), e->ring_hi, e->ring_lo, P, sl, fmt));
         }
     } else {
         return fail(VOSPROP_ERR_INVALID, "unknown layout %d", layout);
     }
     VOS_CUDA(cudaGetLastError());
-    e->slot_frame[slot] = frame_idx;
-    e->slot_labels[slot] = 0;
+    for (int i = 0; i < n; ++i) {
+        const int slot = (first_frame + i) % e->cfg.ring_slots;
+        e->slot_frame[slot] = first_frame + i;
+        e->slot_labels[slot] = 0;
+    }
     e->launches++;
     return VOSPROP_OK;
+}
+
+int vosprop_append_features(vosprop_engine* e, int32_t frame_idx, const void* features, int32_t dtype,
+                            int32_t layout, void* stream) {
+    return append_batch(e, frame_idx, 1, features, dtype, layout, static_cast<cudaStream_t>(stream));
 }
 
 static int labels_target(vosprop_engine* e, int frame_idx, float** meta_slot, int kind) {
@@ -517,15 +525,12 @@ int vosprop_append_frames(vosprop_engine* e, int32_t first_frame_idx, int32_t n_
     if (!e) return fail(VOSPROP_ERR_INVALID, "null engine");
     if (n_frames < 0 || n_frames > e->cfg.ring_slots)
         return fail(VOSPROP_ERR_INVALID, "n_frames=%d outside 0..ring_slots=%d", n_frames, e->cfg.ring_slots);
-    if (dtype != VOSPROP_F32 && dtype != VOSPROP_F16 && dtype != VOSPROP_BF16) return fail(VOSPROP_ERR_INVALID, "unknown dtype %d", dtype);
-    const size_t frame_bytes = static_cast<size_t>(VOSPROP_FEAT_DIM) * e->P * (dtype == VOSPROP_F32 ? 4 : 2);
-    for (int i = 0; i < n_frames; ++i) {
-        int rc = vosprop_append_features(e, first_frame_idx + i, static_cast<const char*>(features) + i * frame_bytes, dtype, layout, stream);
+    if (n_frames == 0) return VOSPROP_OK;
+    int rc = append_batch(e, first_frame_idx, n_frames, features, dtype, layout, static_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+    for (int i = 0; class_idx && i < n_frames; ++i) {
+        rc = vosprop_set_labels_index(e, first_frame_idx + i, class_idx + static_cast<size_t>(i) * e->P, stream);
         if (rc) return rc;
-        if (class_idx) {
-            rc = vosprop_set_labels_index(e, first_frame_idx + i, class_idx + static_cast<size_t>(i) * e->P, stream);
-            if (rc) return rc;
-        }
     }
     return VOSPROP_OK;
 }

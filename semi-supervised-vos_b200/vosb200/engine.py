@@ -14,7 +14,7 @@ import torch
 from . import _capi as capi
 
 CONTINUOUS_FRAME = 4          # src/config.py:13
-DEFAULT_RING_SLOTS = 48       # >= frame_range(40) + CONTINUOUS_FRAME + 1, SURVEY.md P5
+DEFAULT_RING_SLOTS = 64       # frame_range(40) + CONTINUOUS_FRAME + 1 = 45 resident frames + 19 appended ahead
 
 _DTYPES = {torch.float32: capi.F32, torch.float16: capi.F16, torch.bfloat16: capi.BF16}
 
@@ -183,17 +183,27 @@ class PropagationEngine:
                                                      _DTYPES[features.dtype], layout, self._stream()))
         features.record_stream(torch.cuda.current_stream(self.device))
 
+    def lookahead(self, frame_range: int, ref_num: int) -> int:
+        """How many frames may sit in the ring ahead of the frame being propagated (the target included) without
+        overwriting a frame sample_frames can still pick: ring_slots - required_ring_slots + 1 (>= 1)."""
+        return max(1, self.ring_slots - required_ring_slots(frame_range, ref_num) + 1)
+
     @_on_device
     def append_frames(self, first_frame_idx: int, features: torch.Tensor, class_idx: Optional[torch.Tensor] = None):
-        """features: (n,K,H_d,W_d) contiguous fp32/fp16/bf16 -> frames first_frame_idx .. +n-1; class_idx: optional
-        (n,H_d,W_d) / (n,P) uint8 index labels for all of them (one call installs a labelled clip)."""
+        """features: (n,K,H_d,W_d) fp32/fp16/bf16, standard or channels_last -> frames first_frame_idx .. +n-1 in ONE
+        launch; class_idx: optional (n,H_d,W_d) / (n,P) uint8 index labels for all of them (one call installs a labelled clip)."""
         H_d, W_d = self.geom[0], self.geom[1]
         n = features.shape[0]
         if tuple(features.shape[1:]) != (capi.FEAT_DIM, H_d, W_d):
             raise ValueError(f'expected (n,{capi.FEAT_DIM},{H_d},{W_d}) features, got {tuple(features.shape)}')
         if features.dtype not in _DTYPES or not features.is_cuda:
             raise TypeError(f'features must be a CUDA fp32/fp16/bf16 tensor, got {features.dtype} on {features.device}')
-        features = features.contiguous()
+        if features.is_contiguous():
+            layout = capi.NCHW
+        elif features.permute(0, 2, 3, 1).is_contiguous():
+            layout = capi.NHWC
+        else:
+            features, layout = features.contiguous(), capi.NCHW
         cls_ptr = None
         if class_idx is not None:
             class_idx = class_idx.reshape(n, -1).to(device=self.device, dtype=torch.uint8).contiguous()
@@ -201,7 +211,7 @@ class PropagationEngine:
                 raise ValueError(f'expected {H_d * W_d} labels per frame, got {class_idx.shape[1]}')
             cls_ptr = C.c_void_p(class_idx.data_ptr())
         capi.check(self._lib.vosprop_append_frames(self._h, first_frame_idx, n, C.c_void_p(features.data_ptr()),
-                                                   _DTYPES[features.dtype], capi.NCHW, cls_ptr, self._stream()))
+                                                   _DTYPES[features.dtype], layout, cls_ptr, self._stream()))
         features.record_stream(torch.cuda.current_stream(self.device))
         if class_idx is not None:
             class_idx.record_stream(torch.cuda.current_stream(self.device))

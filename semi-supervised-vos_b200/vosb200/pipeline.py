@@ -43,7 +43,7 @@ class ClipSegmenter:
         self.copy_stream = torch.cuda.Stream(self.device)
 
     def _ensure_engine(self, n_pixels: int):
-        slots = max(required_ring_slots(self.params['frame_range'], self.params['ref_num']), 48)
+        slots = required_ring_slots(self.params['frame_range'], self.params['ref_num']) + 19     # 19 frames appended ahead
         if self.engine is None or self.engine.max_pixels < n_pixels or self.engine.ring_slots < slots:
             if self.engine is not None:
                 self.engine.close()
@@ -96,13 +96,18 @@ class ClipSegmenter:
             if raw:
                 cur = normalize_frames(cur, torch.float16 if self.amp else torch.float32)
             feats = self.embed(cur)
+            appended = 0                     # frames of this batch already in the ring
             for i in range(feats.shape[0]):
                 t = b0 + i
                 if t == 0:
                     self._ensure_engine(feats.shape[2] * feats.shape[3])
                     start_sequence(self.engine, feats[0], first_label.to(self.device, non_blocking=True))
+                    appended = 1
                     continue
-                self.engine.append(t, feats[i])
+                if i >= appended:            # one launch appends the next frames of the batch (engine.lookahead)
+                    n = min(self.engine.lookahead(p['frame_range'], p['ref_num']), feats.shape[0] - appended)
+                    self.engine.append_frames(t, feats[appended:appended + n])
+                    appended += n
                 self.engine.step(t, p['frame_range'], p['ref_num'], p['sigma_1'], p['sigma_2'], p['temperature'],
                                  p['probability_propagation'], kernel=self.kernel, want_prediction=False,
                                  want_lowres=False, want_fullres=False, out_fullres=masks_dev[t - 1])

@@ -62,8 +62,13 @@ def propagate_clip(engine: PropagationEngine, features: torch.Tensor, first_labe
     P = features.shape[2] * features.shape[3]
     masks = torch.empty((max(T - 1, 0), H, W), dtype=torch.uint8, device=engine.device)
     preds = torch.empty((T - 1, d, P), dtype=torch.float32, device=engine.device) if return_predictions else None
+    ahead = engine.lookahead(frame_range, ref_num)
+    appended = 1                         # frames 0 .. appended-1 are in the ring
     for t in range(1, T):
-        engine.append(t, features[t])
+        if t >= appended:                # one launch appends the next `ahead` frames: off the per-frame chain
+            n = min(ahead, T - appended)
+            engine.append_frames(appended, features[appended:appended + n])
+            appended += n
         engine.step(t, frame_range, ref_num, sigma_1, sigma_2, temperature, probability_propagation,
                     kernel=kernel, want_prediction=False, want_lowres=False, want_fullres=False,
                     out_fullres=masks[t - 1], out_prediction=preds[t - 1] if return_predictions else None, topk=topk)
@@ -79,8 +84,9 @@ def propagate_clips_lanes(engines: Sequence[PropagationEngine], clips, sigma_1: 
     Frames inside a sequence are strictly serial (the labels of frame t feed frame t+1), and the fused affinity kernel
     of one sequence fills every SM.  The lanes advance round-robin, one frame each, and their affinity kernels are
     chained through events (vosprop_step.wait_event / record_event) so they run back to back on the device while the
-    other lanes' launch latencies and small kernels fill the gaps.  (The small kernels do not co-reside with a resident
-    affinity CTA today: 5 of its 18 warps x 96 registers fill two of the four scheduler partitions' register files.)  clips: [(features (T,K,H_d,W_d), first annotation (H,W), d or None), ...].
+    other lanes' launch latencies and small kernels fill the gaps.  (Measured in round 2, DESIGN.md section 10: more sequences in
+    flight do not pay on this GPU -- merges that run under the other sequence's fused kernel are won back by its slower tiles,
+    two reference memories no longer fit the part of the L2 one die can use.)  clips: [(features (T,K,H_d,W_d), first annotation (H,W), d or None), ...].
     Returns one (T-1,H,W) uint8 device tensor per clip.  No host sync inside; the current stream waits for the lanes."""
     n_lanes = len(engines)
     dev = engines[0].device
@@ -93,6 +99,7 @@ def propagate_clips_lanes(engines: Sequence[PropagationEngine], clips, sigma_1: 
     lanes = [[i for i in range(len(clips)) if i % n_lanes == lane] for lane in range(n_lanes)]
     outs = [None] * len(clips)
     cursor = [[0, 0] for _ in range(n_lanes)]         # per lane: (position in its clip list, next frame)
+    appended = [1] * n_lanes                          # per lane: frames of its current clip already in the ring
     prev_event = None
     busy = True
     while busy:
@@ -111,8 +118,12 @@ def propagate_clips_lanes(engines: Sequence[PropagationEngine], clips, sigma_1: 
                     start_sequence(eng, feats[0], first_t, d)
                     H, W = first_t.shape
                     outs[ci] = torch.empty((feats.shape[0] - 1, H, W), dtype=torch.uint8, device=dev)
+                    appended[lane] = 1
                 else:
-                    eng.append(t, feats[t])
+                    if t >= appended[lane]:           # one launch appends the next frames (engine.lookahead)
+                        n = min(eng.lookahead(frame_range, ref_num), feats.shape[0] - appended[lane])
+                        eng.append_frames(appended[lane], feats[appended[lane]:appended[lane] + n])
+                        appended[lane] += n
                     eng.step(t, frame_range, ref_num, sigma_1, sigma_2, temperature, probability_propagation, kernel=kernel,
                              want_prediction=False, want_lowres=False, want_fullres=False, out_fullres=outs[ci][t - 1],
                              topk=topk, wait_event=prev_event, record_event=events[lane])
@@ -122,3 +133,4 @@ def propagate_clips_lanes(engines: Sequence[PropagationEngine], clips, sigma_1: 
     for s in streams:
         main.wait_stream(s)
     return outs
+

@@ -156,6 +156,41 @@ def test_append_frames_equals_per_frame_appends():
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize('layout', ['nchw', 'nhwc'])
+@pytest.mark.parametrize('dtype', [torch.float16, torch.float32])
+def test_batched_append_wraps_the_ring_like_single_appends(layout, dtype):
+    """One launch for a batch of frames (grid z = frame) writes ring slot (first + i) % ring_slots of every frame, also
+    across the wrap, from standard and channels-last sources: the propagated distribution is bit-identical to per-frame
+    appends, and propagate_clip (which appends `engine.lookahead` frames ahead) to the per-frame loop."""
+    from vosb200 import PropagationEngine
+    from vosb200.engine import plan_refs
+    torch.manual_seed(3)
+    T, S = 15, 12
+    f = (torch.randn(T, 256, 16, 40, device='cuda') * 0.3).to(dtype)
+    if layout == 'nhwc':
+        f = f.contiguous(memory_format=torch.channels_last)
+    c = torch.randint(0, 3, (T, 16 * 40), device='cuda', dtype=torch.uint8)
+    prec = 1 if dtype == torch.float16 else 0
+    outs = []
+    for batched in (False, True):
+        eng = PropagationEngine(max_pixels=640, ring_slots=S)
+        eng.reset(16, 40, 128, 320, 3, prec)
+        if batched:
+            eng.append_frames(0, f[:9], c[:9])
+            eng.append_frames(9, f[9:T])                 # slots 9, 10, 11, 0, 1, 2: wraps
+        else:
+            for t in range(T):
+                eng.append(t, f[t])
+                if t < 9:
+                    eng.set_labels_index(t, c[t])
+        for t in range(9, T - 1):
+            eng.set_labels_index(t, c[t])
+        refs = [4, 5, 6, 8, 10, 11, 12, 13]              # frames 4 .. 13 are resident (3 was overwritten by 15 - 12)
+        outs.append(eng.propagate(T - 1, refs, [8.0] * len(refs), write_labels=False)['prediction'].clone())
+        eng.close()
+    assert torch.equal(outs[0], outs[1])
+
+
 def _loader(root, bs):
     from src.utils.datasets import TrainDataset
     ds = TrainDataset(root / 'JPEGImages/480p', root / 'Annotations/480p', frame_num=10, color_jitter=False)

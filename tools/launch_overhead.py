@@ -13,7 +13,7 @@ from vosb200 import PREC_F16, PropagationEngine, plan_refs, synthetic  # noqa: E
 
 def main():
     dev = torch.device('cuda', 0)
-    T, N = 20, 200
+    T, N = 20, 400
     feats, first = synthetic.clip_features(T, 480, 854, 2, seed=1, device=dev)
     P = feats.shape[2] * feats.shape[3]
     f = feats.half()
@@ -37,15 +37,33 @@ def main():
     eng.enable_timing(0)
     a = tm['affinity'][0] / tm['affinity'][1] * 1e3
     m = tm['merge'][0] / tm['merge'][1] * 1e3
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(N):
-        eng.propagate(T - 1, refs, sig, **kw)
-    e1.record()
-    torch.cuda.synchronize()
-    tot = e0.elapsed_time(e1) / N * 1e3
-    print(f'per-launch events: affinity {a:.1f} us  merge {m:.1f} us   |  back-to-back: {tot:.1f} us per (affinity + merge) step', flush=True)
+    def chain(append=False, merge=True, **kws):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(N):
+            if append:
+                eng.append(T - 1, f[T - 1])
+            eng.propagate(T - 1, refs, sig, **kws)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / N * 1e3
+
+    print(f'per-launch events: affinity {a:.1f} us  merge {m:.1f} us', flush=True)
+    full = torch.empty((480, 854), dtype=torch.uint8, device=dev)
+    kw2 = dict(kw, write_labels=True)
+    variants = [('affinity + merge (no outputs)', dict(kw)),
+                ('affinity + merge + ring labels', kw2),
+                ('affinity + merge + full-resolution mask', dict(kw, out_fullres=full)),
+                ('affinity + merge + labels + mask (the clip loop)', dict(kw2, out_fullres=full)),
+                ('append + affinity + merge + labels + mask (round-2 loop)', dict(kw2, out_fullres=full, append=True))]
+    for _ in range(3):          # warm clocks
+        chain(**variants[0][1])
+    res = {name: [] for name, _ in variants}
+    for rep in range(4):        # interleaved repeats: clock / power drift shows as spread, not as a difference between variants
+        for name, kws in variants:
+            res[name].append(chain(**kws))
+    for name, v in res.items():
+        print(f'  chain {name}: ' + ' '.join(f'{x:.1f}' for x in v) + ' us per step', flush=True)
     eng.close()
 
 
