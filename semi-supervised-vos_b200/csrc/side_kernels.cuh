@@ -31,7 +31,9 @@ constexpr int kMergeThreads = 512;    // 64 pixel groups of 8 lanes
 constexpr int kMergeSplit = 2;        // blocks per low-resolution row (column halves): 120 blocks at 480p instead of 60 on 148 SMs
 constexpr int kMergeLanes = 8;        // lanes cooperating on one target pixel
 
-template <int kCap>   // class capacity of this instantiation: kMetaClasses (the product path) or kCap
+constexpr int kMergeSmall = 6;        // class capacity of the small instantiation (DAVIS: at most 5 objects + background)
+
+template <int kCap>   // class capacity of this instantiation: kMergeSmall, kMetaClasses or kMaxClasses
 __global__ void __launch_bounds__(kMergeThreads) vos_merge_writeback(const MergeParams prm) {
     extern __shared__ uint8_t row_cls[];  // [w_lowres]
     pdl_launch_dependents();
@@ -71,26 +73,38 @@ __global__ void __launch_bounds__(kMergeThreads) vos_merge_writeback(const Merge
             pdl_wait();                   // the affinity kernel's partials (and everything before it) are complete
             waited = true;
         }
-        // two passes over this lane's records: the maximum first, then the weighted sums -- every load is independent of
-        // the arithmetic on the previous record
+        // All of this lane's records are fetched in ONE batch of independent loads (absent records read the buffer's first
+        // record and are zeroed afterwards), then folded in the order j = 0..3: a single L2 round trip on the chain
+        // affinity -> merge -> affinity.  (Loads under a per-record branch were issued one record after the other: four
+        // dependent round trips.)
         float M = kNegBig, L = 0.f, acc[kCap];
-#pragma unroll
-        for (int k = 0; k < kCap; ++k) acc[k] = 0.f;
-        float m_r[kMaxRec];
+        float m_r[kMaxRec], l_r[kMaxRec], a_r[kMaxRec][kCap];
 #pragma unroll
         for (int j = 0; j < kMaxRec; ++j) {
-            m_r[j] = recs[j] ? recs[j][0] : kNegBig;
-            M = fmaxf(M, m_r[j]);
+            const float* rp = recs[j] ? recs[j] : prm.partials;
+            m_r[j] = __ldcg(rp);
+            l_r[j] = __ldcg(rp + kTile);
+#pragma unroll
+            for (int k = 0; k < kCap; ++k) a_r[j][k] = (k < prm.d) ? __ldcg(rp + (2 + k) * kTile) : 0.f;
         }
 #pragma unroll
         for (int j = 0; j < kMaxRec; ++j) {
-            if (recs[j]) {
-                const float w = vosptx::ex2(m_r[j] - M);
-                L = fmaf(recs[j][kTile], w, L);
+            if (!recs[j]) {
+                m_r[j] = kNegBig;
+                l_r[j] = 0.f;
 #pragma unroll
-                for (int k = 0; k < kCap; ++k)
-                    if (k < prm.d) acc[k] = fmaf(recs[j][(2 + k) * kTile], w, acc[k]);
+                for (int k = 0; k < kCap; ++k) a_r[j][k] = 0.f;
             }
+            M = fmaxf(M, m_r[j]);
+        }
+#pragma unroll
+        for (int k = 0; k < kCap; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMaxRec; ++j) {
+            const float w = vosptx::ex2(m_r[j] - M);       // absent record: its sums are exact zeros, L and acc stay as they are
+            L = fmaf(l_r[j], w, L);
+#pragma unroll
+            for (int k = 0; k < kCap; ++k) acc[k] = fmaf(a_r[j][k], w, acc[k]);
         }
         for (int i = sublane + kMaxRec * kMergeLanes; i < n_rec; i += kMergeLanes) {      // (very long segment lists only)
             const int c = c_first + (i >> sub_shift), h = i & (prm.n_sub - 1);
@@ -111,8 +125,7 @@ __global__ void __launch_bounds__(kMergeThreads) vos_merge_writeback(const Merge
             const float w_a = vosptx::ex2(M - M_new), w_b = vosptx::ex2(M_o - M_new);
             L = fmaf(__shfl_xor_sync(gmask, L, off), w_b, L * w_a);
 #pragma unroll
-            for (int k = 0; k < kCap; ++k)
-                if (k < prm.d) acc[k] = fmaf(__shfl_xor_sync(gmask, acc[k], off), w_b, acc[k] * w_a);
+            for (int k = 0; k < kCap; ++k) acc[k] = fmaf(__shfl_xor_sync(gmask, acc[k], off), w_b, acc[k] * w_a);   // rows >= d: zeros
             M = M_new;
         }
         if (sublane != 0) continue;
@@ -131,9 +144,13 @@ __global__ void __launch_bounds__(kMergeThreads) vos_merge_writeback(const Merge
         }
         if (prm.write_labels) {
             if constexpr (kCap <= kMetaClasses) {   // wider class sets live in the class bytes only
+                float rec_v[kMetaClasses];          // the whole record, also the classes beyond this instantiation's capacity
 #pragma unroll
-                for (int k = 0; k < kCap; ++k)
-                    mrec[k] = (k < prm.d) ? (prm.probability ? acc[k] : (k == best ? 1.f : 0.f)) : 0.f;
+                for (int k = 0; k < kMetaClasses; ++k)
+                    rec_v[k] = (k < kCap && k < prm.d) ? (prm.probability ? acc[k < kCap ? k : 0] : (k == best ? 1.f : 0.f)) : 0.f;
+#pragma unroll
+                for (int k = 0; k < kMetaClasses; k += 2)          // the record's class part starts 8 bytes into a 64-byte record
+                    *reinterpret_cast<float2*>(mrec + k) = make_float2(rec_v[k], rec_v[k + 1]);
             }
             prm.cls[static_cast<size_t>(prm.q_slot) * prm.p_pad + pix] = static_cast<uint8_t>(best);
         }

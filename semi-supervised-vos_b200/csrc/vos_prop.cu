@@ -632,7 +632,8 @@ int vosprop_propagate(vosprop_engine* e, const vosprop_step* s, void* stream) {
     mp.out_prediction = s->out_prediction; mp.out_mask_lowres = s->out_mask_lowres; mp.out_mask_fullres = s->out_mask_fullres;
     {
         TimedLaunch timed(e, VOSPROP_T_MERGE, st);
-        VOS_CUDA(launch_pdl(e->d > vosk::kMetaClasses ? vosk::vos_merge_writeback<vosk::kMaxClasses> : vosk::vos_merge_writeback<vosk::kMetaClasses>,
+        VOS_CUDA(launch_pdl(e->d > vosk::kMetaClasses ? vosk::vos_merge_writeback<vosk::kMaxClasses>
+                            : e->d > vosk::kMergeSmall ? vosk::vos_merge_writeback<vosk::kMetaClasses> : vosk::vos_merge_writeback<vosk::kMergeSmall>,
                             dim3(e->H_d, vosk::kMergeSplit), vosk::kMergeThreads, e->W_d, st, mp));
     }
     VOS_CUDA(cudaGetLastError());

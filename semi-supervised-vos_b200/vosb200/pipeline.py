@@ -4,7 +4,8 @@ End-to-end path of one clip on one GPU:
   pinned host frames (decoded uint8 RGB, or already normalised fp32) --H2D (copy stream, batch ahead)--> normalisation on the
   GPU for uint8 input (vosprop_normalize_u8: 4x less PCIe traffic than fp32 frames) --> VOSNet on cuDNN (fp16 autocast, as the
   reference does on CUDA: inference_utils.py:35,52; channels_last) --> per frame: ring append +
-  fused propagation (libvosprop) --> uint8 masks accumulate on the device --> one D2H per clip.
+  fused propagation (libvosprop) --> uint8 masks accumulate on the device --> one D2H per clip (its own stream: the copy
+  runs behind the next clip's compute).
 Feature extraction does not depend on propagation state, so frames go through
 the backbone in batches while propagation stays strictly sequential.  No host sync inside a clip.
 """
@@ -41,6 +42,8 @@ class ClipSegmenter:
         self.kernel = kernel
         self.engine: Optional[PropagationEngine] = None
         self.copy_stream = torch.cuda.Stream(self.device)
+        self.d2h_stream = torch.cuda.Stream(self.device)      # masks -> host; apart from the H2D stream: the two directions overlap
+        self._d2h_done: Optional[torch.cuda.Event] = None
 
     def _ensure_engine(self, n_pixels: int):
         slots = required_ring_slots(self.params['frame_range'], self.params['ref_num']) + 19     # 19 frames appended ahead
@@ -62,7 +65,8 @@ class ClipSegmenter:
                 sync: bool = True) -> torch.Tensor:
         """frames: (T,H,W,3) uint8 decoded RGB (normalised on the GPU like datasets.py:128-131) or (T,3,H,W) fp32 already
         normalised; pinned host or device.  first_label (H,W) integer class map.
-        Returns masks for frames 1..T-1 as (T-1,H,W) uint8 in pinned host memory."""
+        Returns masks for frames 1..T-1 as (T-1,H,W) uint8 in pinned host memory.  sync = False: the copy to the host may
+        still be in flight on return (wait() or a device synchronise completes it)."""
         raw = frames.dtype == torch.uint8
         if raw:
             T, H, W, _ = frames.shape
@@ -85,6 +89,9 @@ class ClipSegmenter:
 
         masks_dev = torch.empty((T - 1, H, W), dtype=torch.uint8, device=self.device)
         nxt = stage(0)
+        # class count of the clip (predict.py:113) from the host copy of the annotation when there is one: .item() on a device
+        # tensor would stall the host on everything queued so far, once per clip
+        d = int(first_label.max()) + 1 if not first_label.is_cuda else None
         p = self.params
         for b0 in range(0, T, B):
             cur = nxt
@@ -101,7 +108,7 @@ class ClipSegmenter:
                 t = b0 + i
                 if t == 0:
                     self._ensure_engine(feats.shape[2] * feats.shape[3])
-                    start_sequence(self.engine, feats[0], first_label.to(self.device, non_blocking=True))
+                    start_sequence(self.engine, feats[0], first_label.to(self.device, non_blocking=True), d=d)
                     appended = 1
                     continue
                 if i >= appended:            # one launch appends the next frames of the batch (engine.lookahead)
@@ -113,7 +120,20 @@ class ClipSegmenter:
                                  want_lowres=False, want_fullres=False, out_fullres=masks_dev[t - 1])
         if out is None:
             out = torch.empty((T - 1, H, W), dtype=torch.uint8, pin_memory=True)
-        out.copy_(masks_dev, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(self.d2h_stream):
+            self.d2h_stream.wait_event(ready)
+            out.copy_(masks_dev, non_blocking=True)
+            masks_dev.record_stream(self.d2h_stream)
+            self._d2h_done = torch.cuda.Event()
+            self._d2h_done.record(self.d2h_stream)
         if sync:
-            main.synchronize()
+            self.wait()
         return out
+
+    def wait(self):
+        """Blocks until the masks of the last segment(..., sync=False) call are in host memory."""
+        if self._d2h_done is not None:
+            self._d2h_done.synchronize()
+            self._d2h_done = None

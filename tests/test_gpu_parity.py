@@ -223,3 +223,28 @@ def test_clip_segmenter_end_to_end_matches_stepwise_engine():
     agree = float((masks.cuda() == want).float().mean())
     print(f'ClipSegmenter vs stepwise: {agree:.6f}')
     assert agree >= MASK_AGREE
+
+
+def test_clip_segmenter_async_copy_back_equals_synchronous_call():
+    """segment(sync=False) returns while the masks are still on their way to the host (own D2H stream, behind the next
+    clip's compute); wait() / a device synchronise completes them.  Several clips queued back to back -- uint8 frames and
+    fp32 normalised ones -- give the masks of one synchronous call per clip, bit for bit."""
+    from oracle.fixtures import seeded_state_dict
+    from src.model.vos_net import VOSNet
+    from vosb200 import synthetic
+    from vosb200.pipeline import ClipSegmenter
+    net = VOSNet('resnet50', pretrained=False).eval()
+    net.load_state_dict(seeded_state_dict(net.state_dict()))
+    seg = ClipSegmenter(net, backbone_batch=4)
+    clips = [synthetic.clip_frames(7 + i, 256, 320, 1 + i % 3, seed=11 + i, device='cuda', raw=(i % 2 == 0)) for i in range(4)]
+    want = [seg.segment(f, first).clone() for f, first in clips]
+    outs = [torch.empty((f.shape[0] - 1, 256, 320), dtype=torch.uint8, pin_memory=True) for f, _ in clips]
+    for (f, first), out in zip(clips, outs):
+        got = seg.segment(f, first, out=out, sync=False)
+        assert got is out
+    seg.wait()                       # the last clip's copy: D2H copies run in order on one stream, so all of them
+    for i, (w, o) in enumerate(zip(want, outs)):
+        assert torch.equal(w, o), f'clip {i}'
+    # a device-side first annotation takes the class count from the device (one host sync), same masks
+    f, first = clips[1]
+    assert torch.equal(seg.segment(f, first.cuda()), want[1])
