@@ -225,6 +225,9 @@ __device__ __forceinline__ void idx_role_mma(const IdxPipe& pp, const AffinityPa
         prm.dbg_clk[blockIdx.x * 16 + 6] = static_cast<long long>(ns_end - ns_begin);
         prm.dbg_clk[blockIdx.x * 16 + 7] = static_cast<long long>(ns_begin);
         prm.dbg_clk[blockIdx.x * 16 + 8] = static_cast<long long>(ns_end);
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        prm.dbg_clk[blockIdx.x * 16 + 9] = static_cast<long long>(smid);
     }
 #else
     (void)t_q; (void)t_acc; (void)t_full; (void)t_begin;

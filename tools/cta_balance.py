@@ -28,7 +28,7 @@ def main():
     eng.append_frames(1, f[1:T])
     buf = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
     out = torch.empty((480, 854), dtype=torch.uint8, device=dev)
-    durs = []
+    durs, starts, own, smids = [], [], [], None
     for t in range(1, T):
         if t >= 30:
             capi.check(capi.lib().vosprop_debug_clocks(eng._h, buf.data_ptr()))
@@ -37,6 +37,9 @@ def main():
             torch.cuda.synchronize()
             v = buf.view(148, 16).cpu()
             durs.append((v[:, 8] - v[:, 7].min()).double() / 1e3)        # end of each CTA relative to the first start (us)
+            starts.append((v[:, 7] - v[:, 7].min()).double() / 1e3)      # start skew of each CTA (us)
+            own.append(v[:, 6].double() / 1e3)                           # each CTA's own duration (us)
+            smids = v[:, 9]
     d = torch.stack(durs)                                                   # (launches, 148)
     grid = C.c_int32()
     begins = (C.c_int64 * 149)()
@@ -47,6 +50,14 @@ def main():
     nseg = torch.tensor([(begins[c + 1] - 1) // nt - begins[c] // nt + 1 for c in range(148)])
     print('launch end per CTA (us): mean over CTAs %.1f, min %.1f, max %.1f (per launch: max - mean = %s)' %
           (d.mean(), d.min(), d.max(), ' '.join(f'{float(x):.1f}' for x in (d.max(1).values - d.mean(1)))))
+    s_, o_ = torch.stack(starts), torch.stack(own)
+    print('start skew per CTA (us): mean %.2f, max %.2f; own duration: mean %.1f, min %.1f, max %.1f, std over CTAs of the mean %.2f' %
+          (s_.mean(), s_.max(), o_.mean(), o_.min(), o_.max(), o_.mean(0).std()))
+    print('correlation over CTAs (means over launches): end vs start %.2f, end vs own duration %.2f' %
+          (float(torch.corrcoef(torch.stack([d.mean(0), s_.mean(0)]))[0, 1]), float(torch.corrcoef(torch.stack([d.mean(0), o_.mean(0)]))[0, 1])))
+    print('SM id of each CTA:', smids.tolist())
+    print('mean own duration by CTA:', [round(float(x), 1) for x in o_.mean(0)])
+    print('mean start by CTA:', [round(float(x), 1) for x in s_.mean(0)])
     m = d.mean(0)
     print('mean end by segments in the range: ' + ', '.join(f'{k} seg: {float(m[nseg == k].mean()):.1f} us ({int((nseg == k).sum())} CTAs)' for k in sorted(set(nseg.tolist()))))
     c = torch.corrcoef(d)          # correlation of the per-CTA pattern between launches
