@@ -13,7 +13,7 @@ at the end of the run.  --workload ytvos: configs[4]; --workload uniform: the we
 
   value : propagation-stage throughput (ring append + fused affinity/softmax/prior/gather kernel +
           merge/write-back), stride-8 embeddings already resident in HBM, timed with CUDA events.
-  e2e   : the same metric through the public API (vosb200.pipeline.ClipSegmenter.segment): frames in
+  e2e   : the same metric through the public API (vosb200.pipeline.ClipSegmenterPool.segment_many -> ClipSegmenter.segment): frames in
           pinned host memory -> H2D -> VOSNet on cuDNN -> propagation -> uint8 masks -> D2H, per step.
   roofline     : the fused affinity kernel against the measured bf16 tensor peak (algorithmic FLOPs
                  2*P*(R*P)*K per launch, CUDA events around every launch of the timed region).
@@ -68,6 +68,9 @@ def parse_args():
     ap.add_argument('--lanes', type=int, default=1,
                     help='sequences in flight per GPU (one engine + stream each; 2 gives +2-3 %% frames/s but the lanes\' small '
                          'kernels delay the start of the other lane\'s fused kernel, so its per-launch time reads higher)')
+    ap.add_argument('--e2e-lanes', type=int, default=3,
+                    help='clips in flight per GPU on the end-to-end path (ClipSegmenterPool: one ClipSegmenter, engine and stream each; the '
+                         'other clips\' kernels fill the tails of the first one\'s launches: 2 110 / 2 167 / 2 184 frames/s for 1 / 2 / 3 lanes on one box, identical masks)')
     ap.add_argument('--no-kernel-events', action='store_true', help='do not bracket every kernel with CUDA events (roofline fields become null)')
     ap.add_argument('--block-skip', choices=['auto', 'on', 'off'], default='auto',
                     help='exact skipping of affinity blocks below fp32 underflow (vosprop_block_skip; auto = the engine default: it probes '
@@ -118,8 +121,9 @@ def workload_config(args, n_gpus, seqs, assignment, imbalance):
                           'fp32 embeddings: bf16x3 split (hi*hi + lo*hi + hi*lo) tcgen05, fp32 accumulate/softmax'),
             'l2': 'inputs larger than L2 (3.3 MB of fp16 embeddings per frame, > 1 GB per step per GPU; 126 MB L2)',
             'value_scope': 'propagation stage: append + fused affinity + merge/write-back; embeddings resident in HBM',
-            'e2e_scope': 'ClipSegmenter.segment: pinned host uint8 frames -> H2D -> normalise (vosprop_normalize_u8) -> VOSNet(cuDNN, fp16) '
-                         '-> propagation -> uint8 masks -> D2H per sequence; one NCCL gather of all masks to rank 0 at the end of the run'}
+            'e2e_scope': 'ClipSegmenterPool.segment_many, %d clips in flight per GPU, each through ClipSegmenter.segment: pinned host uint8 '
+                         'frames -> H2D -> normalise (vosprop_normalize_u8) -> VOSNet(cuDNN, fp16) -> propagation -> uint8 masks -> D2H per '
+                         'sequence (own stream); one NCCL gather of all masks to rank 0 at the end of the run' % max(1, args.e2e_lanes)}
 
 
 class ClockSampler:
@@ -301,7 +305,7 @@ def traffic_bytes(precision):
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from vosb200 import PropagationEngine, shard, synthetic
-    from vosb200.pipeline import ClipSegmenter
+    from vosb200.pipeline import ClipSegmenterPool
     from vosb200.sequence import propagate_clip, propagate_clips_lanes
     from src.model.vos_net import VOSNet
 
@@ -464,14 +468,13 @@ def run_ours(args, rank, world, local_rank):
     if not args.no_e2e:
         torch.manual_seed(0)
         net = VOSNet('resnet50', pretrained=False)
-        seg = ClipSegmenter(net, device=dev, sigma_1=SIGMA_1, sigma_2=SIGMA_2, frame_range=FRAME_RANGE, ref_num=REF_NUM,
-                            temperature=TEMPERATURE)
+        pool = ClipSegmenterPool(net, lanes=max(1, args.e2e_lanes), device=dev, sigma_1=SIGMA_1, sigma_2=SIGMA_2, frame_range=FRAME_RANGE,
+                                 ref_num=REF_NUM, temperature=TEMPERATURE)
         host_clips = [synthetic.clip_frames(seqs[i][0], H, W, seqs[i][1], seed=2000 + i, device=dev, raw=True) for i in mine]
         outs = [torch.empty((seqs[i][0] - 1, H, W), dtype=torch.uint8, pin_memory=True) for i in mine]
 
         def e2e_step():
-            for i, (frames, first) in enumerate(host_clips):
-                seg.segment(frames, first, out=outs[i], sync=False)
+            pool.segment_many(host_clips, outs=outs, sync=False)
             torch.cuda.synchronize(dev)     # the masks of the step are in pinned host memory
 
         def final_gather():                 # end of run: the per-sequence results of every rank -> rank 0 (NCCL send/recv)

@@ -248,3 +248,30 @@ def test_clip_segmenter_async_copy_back_equals_synchronous_call():
     # a device-side first annotation takes the class count from the device (one host sync), same masks
     f, first = clips[1]
     assert torch.equal(seg.segment(f, first.cuda()), want[1])
+
+
+def test_clip_segmenter_pool_equals_one_clip_at_a_time():
+    """ClipSegmenterPool: clips in flight on several lanes (own engine + stream each) give the masks of one synchronous
+    ClipSegmenter.segment call per clip, bit for bit -- for 1, 2 and 3 lanes, more clips than lanes, mixed sizes."""
+    from oracle.fixtures import seeded_state_dict
+    from src.model.vos_net import VOSNet
+    from vosb200 import synthetic
+    from vosb200.pipeline import ClipSegmenter, ClipSegmenterPool
+    net = VOSNet('resnet50', pretrained=False).eval()
+    net.load_state_dict(seeded_state_dict(net.state_dict()))
+    sizes = [(256, 320), (192, 256), (256, 320), (200, 264), (256, 320)]
+    clips = [synthetic.clip_frames(6 + 2 * i, h, w, 1 + i % 3, seed=21 + i, device='cuda', raw=(i % 2 == 1))
+             for i, (h, w) in enumerate(sizes)]
+    one = ClipSegmenter(net, backbone_batch=4)
+    want = [one.segment(f, first).clone() for f, first in clips]
+    for lanes in (1, 2, 3):
+        pool = ClipSegmenterPool(net, lanes=lanes, backbone_batch=4)
+        got = pool.segment_many(clips)
+        assert len(got) == len(clips)
+        for i, (w, g) in enumerate(zip(want, got)):
+            assert g.shape == w.shape and torch.equal(w, g), f'lanes {lanes}, clip {i}'
+        outs = [torch.empty_like(w).pin_memory() for w in want]
+        pool.segment_many(clips, outs=outs, sync=False)
+        pool.wait()
+        assert all(torch.equal(w, o) for w, o in zip(want, outs)), f'lanes {lanes}, preallocated outputs'
+        pool.close()
