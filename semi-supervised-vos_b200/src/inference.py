@@ -91,7 +91,8 @@ def inference_command_impl(ref_num, data, resume, model, temperature, frame_rang
         if not videos:
             return
     dataset = InferenceDataset(str(Path(data) / 'JPEGImages/480p'), disable=disable,
-                               inference_strategy=inference_strategy, scale=scale, raw=True, videos=videos)
+                               inference_strategy=inference_strategy, scale=scale,
+                               raw='coef' if os.environ.get('VOS_GPU_JPEG', '1') != '0' else True, videos=videos)
     # the reference decodes with one worker (inference.py:75-78); JPEG decode is the slowest stage once propagation runs on
     # the GPU, so it is spread over workers here (same PIL decode, same order: shuffle=False)
     cpus = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)

@@ -61,9 +61,11 @@ class TrainDataset(datasets.ImageFolder):
 
 
 class InferenceDataset(datasets.ImageFolder):
-    """`raw=True` (what `inference_command_impl` asks for): items carry the decoded frame as a uint8 (H,W,3) tensor instead
-    of the normalised fp32 (3,H,W) one; the loops normalise it on the GPU (vosprop_normalize_u8: same arithmetic, same
-    bits) -- ToTensor + Normalize cost more host time per 480p frame than the JPEG decode."""
+    """`raw=True`: items carry the decoded frame as a uint8 (H,W,3) tensor instead of the normalised fp32 (3,H,W) one; the loops
+    normalise it on the GPU (vosprop_normalize_u8: same arithmetic, same bits) -- ToTensor + Normalize cost more host time per
+    480p frame than the JPEG decode.  `raw='coef'` (what `inference_command_impl` asks for unless VOS_GPU_JPEG=0): items of the
+    strategies that feed the network the frame as decoded carry the frame's quantised DCT coefficients (int16, vosb200/jpeg.py)
+    and the GPU finishes the decode with Pillow's exact pixels; other strategies and other JPEG flavours behave like raw=True."""
 
     def __init__(self, root, transform=None, target_transform=None, disable=False,
                  inference_strategy='single', scale=None, raw=False, videos=None):
@@ -86,6 +88,15 @@ class InferenceDataset(datasets.ImageFolder):
 
     def __getitem__(self, index):
         _, video_index = self.imgs[index]
+        if self.raw == 'coef' and self.inference_strategy in ('single', 'multimodel', '3-scale'):
+            # JPEG front end of libvosprop (vosb200/jpeg.py): the worker does the Huffman half of the decode and ships the
+            # quantised DCT coefficients; de-quantisation, inverse DCT, chroma up-sampling and colour conversion run on the GPU
+            # with Pillow's exact pixels (inference_utils._to_device).  Files outside that path keep Pillow below.
+            from vosb200 import jpeg
+            try:
+                return jpeg.pack_item(self.img_bytes[index]), self.idx_to_class[video_index]
+            except jpeg.Unsupported:
+                pass
         img = Image.open(BytesIO(self.img_bytes[index]))
         if img.mode != 'RGB':                      # convert() copies even when there is nothing to convert (1.6 ms at 480p)
             img = img.convert('RGB')

@@ -139,7 +139,10 @@ _WRITER = _PngWriter()
 def _to_device(input):
     """Loader item -> network input on Config.DEVICE: the reference's normalised fp32 (n,3,H,W) tensor as is, or decoded
     uint8 (n,H,W,3) frames (InferenceDataset(raw=True)) normalised on the GPU -- bit-identical values, a quarter of the
-    bytes over PCIe."""
+    bytes over PCIe -- or int16 (n,L) JPEG coefficient items (raw='coef') decoded to those frames on the GPU first."""
+    if input.dtype == torch.int16:       # InferenceDataset(raw='coef'): Huffman-decoded JPEG coefficients, the GPU finishes the decode
+        from vosb200 import jpeg
+        return normalize_frames(jpeg.unpack_items(input, _require_cuda()), torch.float32)
     input = input.to(_require_cuda(), non_blocking=True)
     if input.dtype == torch.uint8:
         return normalize_frames(input, torch.float32)

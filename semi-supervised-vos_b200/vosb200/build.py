@@ -18,13 +18,13 @@ CSRC = Path(__file__).resolve().parent.parent / 'csrc'
 LIB = CSRC / 'libvosprop.so'
 CLASS_CAPS = (2, 3, 4, 6, 8, 11, 14)
 HEADERS = ['kernels.cuh', 'side_kernels.cuh', 'affinity_idx.cuh', 'affinity_topk.cuh', 'affinity_prob.cuh', 'topk_params.h', 'launch.h', 'ptx.cuh',
-           'decompose.h', '../../include/vos_prop.h']
+           'decompose.h', '../../include/vos_prop.h', '../../include/vos_jpeg.h']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC']
 
 
 def units():
     """(object name, source, extra defines)"""
-    out = [('vos_prop', 'vos_prop.cu', []), ('inst_dispatch', 'inst_dispatch.cu', []), ('inst_topk', 'inst_topk.cu', [])]
+    out = [('vos_prop', 'vos_prop.cu', []), ('inst_dispatch', 'inst_dispatch.cu', []), ('inst_topk', 'inst_topk.cu', []), ('jpeg', 'jpeg.cu', [])]
     for d in CLASS_CAPS + (24,):
         out.append((f'inst_idx_{d}', 'inst_idx.cu', [f'-DVOS_INST_D={d}']))
     for d in CLASS_CAPS:
