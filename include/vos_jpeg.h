@@ -51,6 +51,14 @@ int64_t vosjpeg_scratch_bytes(const vosjpeg_info* info);
  * uint8, the array np.asarray(img.convert('RGB')) holds).  Replaces the reconstruction half of Image.convert('RGB'). */
 int vosjpeg_reconstruct(const vosjpeg_info* info, const int16_t* coef_dev, uint8_t* scratch_dev, uint8_t* rgb_dev, void* stream);
 
+/* The device stage for a batch of frames of ONE geometry (what a video's frames are) in two launches: frame f takes its
+ * coefficients at coef_dev + f * coef_stride (int16 elements) and its quantisation tables ([3][64] uint16, natural order) at
+ * quant_dev + f * quant_stride (device memory, e.g. the `quant` field of each frame's vosjpeg_info copied along with its
+ * coefficients), or info->quant for every frame when quant_dev is NULL.  scratch_dev: n_frames x (vosjpeg_scratch_bytes rounded
+ * up to 8) bytes; rgb_dev: n_frames x height x width x 3. */
+int vosjpeg_reconstruct_batch(const vosjpeg_info* info, int32_t n_frames, const int16_t* coef_dev, int64_t coef_stride,
+                              const uint16_t* quant_dev, int64_t quant_stride, uint8_t* scratch_dev, uint8_t* rgb_dev, void* stream);
+
 /* The same stage on the host (single thread), for files decoded where no GPU is wanted and for the CPU tests of the
  * host code; identical output. */
 int vosjpeg_reconstruct_host(const vosjpeg_info* info, const int16_t* coef, uint8_t* rgb);

@@ -425,11 +425,36 @@ bool valid_info(const vosjpeg_info* info) {
 }
 
 // ---- kernels ----
-// One thread per 8x8 block of any component: 128 bytes of coefficients in, 64 samples out.
-__global__ void __launch_bounds__(128) vosjpeg_idct(const __grid_constant__ ReconParams rp, const int16_t* __restrict__ coef,
-                                                    uint8_t* __restrict__ planes, int64_t n_blocks) {
-    const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (b >= n_blocks) return;
+// A launch handles a batch of frames of one geometry (grid y / z = frame): frame f reads its coefficients at coef + f * coef_stride
+// and its quantisation tables at quant + f * quant_stride (device memory: the loader item's own header), or the geometry's tables
+// when quant is null.
+struct BatchParams {
+    ReconParams rp;
+    int64_t coef_stride;        // int16 elements between frames
+    const uint16_t* quant;      // per-frame tables [3][64] in device memory, or null
+    int64_t quant_stride;       // uint16 elements between frames
+    int64_t scratch_stride;     // bytes
+};
+
+// Eight threads per 8x8 block (32 blocks per CTA): thread r loads and de-quantises row r (16 contiguous bytes: a block's 128
+// bytes are one coalesced line), the eight threads run the column pass (thread = column) and the row pass (thread = row) through
+// shared memory, and thread r stores the 8 samples of row r (the 4 blocks of a warp that are neighbours in x write 32 contiguous
+// bytes per row).  The block's slot is padded to 72 words so that the 4 blocks of a warp fall on different banks.
+constexpr int kIdctBlocksPerCta = 32;
+constexpr int kIdctSlot = 72;
+__global__ void __launch_bounds__(kIdctBlocksPerCta * 8) vosjpeg_idct(const __grid_constant__ BatchParams bp, const int16_t* __restrict__ coef,
+                                                                      uint8_t* __restrict__ planes, int64_t n_blocks) {
+    __shared__ int ws[kIdctBlocksPerCta * kIdctSlot];
+    __shared__ uint16_t qs[3 * 64];
+    const ReconParams& rp = bp.rp;
+    const int f = blockIdx.y;
+    if (threadIdx.x < 3 * 64)
+        qs[threadIdx.x] = bp.quant != nullptr ? __ldg(bp.quant + f * bp.quant_stride + threadIdx.x) : rp.info.quant[threadIdx.x >> 6][threadIdx.x & 63];
+    __syncthreads();
+    const int lb = threadIdx.x >> 3, t = threadIdx.x & 7;
+    const int64_t b = static_cast<int64_t>(blockIdx.x) * kIdctBlocksPerCta + lb;
+    if (b >= n_blocks) return;                       // whole groups of 8 lanes leave together; __syncwarp below names the live lanes
+    const unsigned live = __activemask();
     int c = 0;
     int64_t local = b;
     while (c + 1 < rp.info.n_comp && local >= static_cast<int64_t>(rp.info.blocks_w[c]) * rp.info.blocks_h[c]) {
@@ -437,29 +462,101 @@ __global__ void __launch_bounds__(128) vosjpeg_idct(const __grid_constant__ Reco
         ++c;
     }
     const int by = static_cast<int>(local / rp.info.blocks_w[c]), bx = static_cast<int>(local % rp.info.blocks_w[c]);
-    __align__(16) int16_t blk[64];
-    const uint4* src = reinterpret_cast<const uint4*>(coef + rp.info.coef_offset[c] + local * 64);
+    int* w = ws + lb * kIdctSlot;
+    {   // row t of the coefficient block, de-quantised
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(coef + f * bp.coef_stride + rp.info.coef_offset[c] + local * 64) + t);
+        const int16_t* v = reinterpret_cast<const int16_t*>(&raw);
+        const uint16_t* q = qs + c * 64 + t * 8;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) reinterpret_cast<uint4*>(blk)[i] = __ldg(src + i);
-    __align__(8) uint8_t px[64];
-    idct_block(blk, rp.info.quant[c], px, 8);
-    uint8_t* dst = planes + rp.plane[c].offset + (static_cast<int64_t>(by) * 8) * rp.plane[c].stride + bx * 8;
+        for (int i = 0; i < 8; ++i) w[t * 8 + i] = static_cast<int>(v[i]) * static_cast<int>(q[i]);
+    }
+    __syncwarp(live);
+    int o[8];
+    idct8(w[t], w[8 + t], w[16 + t], w[24 + t], w[32 + t], w[40 + t], w[48 + t], w[56 + t], 11, o);      // column t
+    __syncwarp(live);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) *reinterpret_cast<uint2*>(dst + static_cast<int64_t>(r) * rp.plane[c].stride) = reinterpret_cast<const uint2*>(px)[r];
+    for (int r = 0; r < 8; ++r) w[t * 8 + r] = o[r];                                                     // stored transposed: [column][row]
+    __syncwarp(live);
+    idct8(w[t], w[8 + t], w[16 + t], w[24 + t], w[32 + t], w[40 + t], w[48 + t], w[56 + t], 18, o);      // row t
+    __align__(8) uint8_t px[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) px[i] = idct_limit(o[i]);
+    uint8_t* dst = planes + f * bp.scratch_stride + rp.plane[c].offset + (static_cast<int64_t>(by) * 8 + t) * rp.plane[c].stride + bx * 8;
+    *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(px);
 }
 
-// One thread per pixel: up-sample the chroma planes at (x, y), convert, store 3 bytes.
-__global__ void __launch_bounds__(256) vosjpeg_colour(const __grid_constant__ ReconParams rp, const uint8_t* __restrict__ planes,
-                                                      uint8_t* __restrict__ rgb) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= rp.info.width) return;
-    const int yy = upsampled(planes + rp.plane[0].offset, rp.plane[0], x, y);
-    uint8_t* out = rgb + (static_cast<int64_t>(y) * rp.info.width + x) * 3;
-    if (rp.info.n_comp == 1) {
-        out[0] = out[1] = out[2] = static_cast<uint8_t>(yy);
-        return;
+// Four horizontally adjacent pixels per thread (x0 a multiple of 4): one 32-bit load of luma, the chroma samples of the two source
+// columns and their neighbours once for all four pixels, 12 output bytes (16-bit stores when the row pitch allows).
+struct Chroma4 {
+    int v[4];
+};
+__device__ __forceinline__ Chroma4 upsampled4(const uint8_t* plane, const PlaneGeom& g, int x0, int y, int width) {
+    Chroma4 r;
+    if (g.fh == 1) {
+        const uint8_t* row = plane + static_cast<int64_t>(y) * g.stride + x0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r.v[i] = row[i];          // (the plane is padded to whole MCUs: reads past `width` stay inside it)
+        return r;
     }
-    ycc_rgb(yy, upsampled(planes + rp.plane[1].offset, rp.plane[1], x, y), upsampled(planes + rp.plane[2].offset, rp.plane[2], x, y), out);
+    const int j0 = x0 >> 1;                                   // source columns j0, j0 + 1; neighbours j0 - 1, j0 + 2
+    const int jm = j0 > 0 ? j0 - 1 : 0, j1 = j0 + 1 < g.w ? j0 + 1 : g.w - 1, j2 = j0 + 2 < g.w ? j0 + 2 : g.w - 1;
+    int sm, s0, s1, s2;                                       // column sums (h2v2) or samples (h2v1), scaled alike below
+    if (g.fv == 1) {
+        const uint8_t* row = plane + static_cast<int64_t>(y) * g.stride;
+        sm = row[jm]; s0 = row[j0]; s1 = row[j1]; s2 = row[j2];
+        if (g.w <= 2) {
+            r.v[0] = r.v[1] = s0; r.v[2] = r.v[3] = s1;
+            return r;
+        }
+        r.v[0] = j0 == 0 ? s0 : (3 * s0 + sm + 1) >> 2;
+        r.v[1] = j0 == g.w - 1 ? s0 : (3 * s0 + s1 + 2) >> 2;
+        r.v[2] = (3 * s1 + s0 + 1) >> 2;
+        r.v[3] = j0 + 1 >= g.w - 1 ? s1 : (3 * s1 + s2 + 2) >> 2;
+        return r;
+    }
+    const int i = y >> 1;
+    const uint8_t* row0 = plane + static_cast<int64_t>(i) * g.stride;
+    if (g.w <= 2) {
+        r.v[0] = r.v[1] = row0[j0]; r.v[2] = r.v[3] = row0[j1];
+        return r;
+    }
+    const int io = (y & 1) ? (i + 1 < g.h ? i + 1 : g.h - 1) : (i > 0 ? i - 1 : 0);
+    const uint8_t* row1 = plane + static_cast<int64_t>(io) * g.stride;
+    sm = 3 * row0[jm] + row1[jm]; s0 = 3 * row0[j0] + row1[j0]; s1 = 3 * row0[j1] + row1[j1]; s2 = 3 * row0[j2] + row1[j2];
+    r.v[0] = j0 == 0 ? (4 * s0 + 8) >> 4 : (3 * s0 + sm + 8) >> 4;
+    r.v[1] = j0 == g.w - 1 ? (4 * s0 + 7) >> 4 : (3 * s0 + s1 + 7) >> 4;
+    r.v[2] = (3 * s1 + s0 + 8) >> 4;
+    r.v[3] = j0 + 1 >= g.w - 1 ? (4 * s1 + 7) >> 4 : (3 * s1 + s2 + 7) >> 4;
+    (void)width;
+    return r;
+}
+
+__global__ void __launch_bounds__(128) vosjpeg_colour(const __grid_constant__ BatchParams bp, const uint8_t* __restrict__ planes,
+                                                      uint8_t* __restrict__ rgb) {
+    const ReconParams& rp = bp.rp;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y, f = blockIdx.z;
+    const int width = rp.info.width;
+    if (x0 >= width) return;
+    planes += f * bp.scratch_stride;
+    const uint32_t luma = __ldg(reinterpret_cast<const uint32_t*>(planes + rp.plane[0].offset + static_cast<int64_t>(y) * rp.plane[0].stride + x0));
+    __align__(4) uint8_t px[12];
+    if (rp.info.n_comp == 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) px[3 * i] = px[3 * i + 1] = px[3 * i + 2] = static_cast<uint8_t>((luma >> (8 * i)) & 255u);
+    } else {
+        const Chroma4 cb = upsampled4(planes + rp.plane[1].offset, rp.plane[1], x0, y, width);
+        const Chroma4 cr = upsampled4(planes + rp.plane[2].offset, rp.plane[2], x0, y, width);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ycc_rgb(static_cast<int>((luma >> (8 * i)) & 255u), cb.v[i], cr.v[i], px + 3 * i);
+    }
+    uint8_t* out = rgb + ((static_cast<int64_t>(f) * rp.info.height + y) * width + x0) * 3;
+    const int n = width - x0 < 4 ? width - x0 : 4;
+    if (n == 4 && (reinterpret_cast<uintptr_t>(out) & 1) == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) reinterpret_cast<uint16_t*>(out)[i] = reinterpret_cast<const uint16_t*>(px)[i];
+    } else {
+        for (int i = 0; i < 3 * n; ++i) out[i] = px[i];
+    }
 }
 
 }  // namespace
@@ -562,18 +659,32 @@ int64_t vosjpeg_scratch_bytes(const vosjpeg_info* info) {
     return total;
 }
 
-int vosjpeg_reconstruct(const vosjpeg_info* info, const int16_t* coef_dev, uint8_t* scratch_dev, uint8_t* rgb_dev, void* stream) {
+int vosjpeg_reconstruct_batch(const vosjpeg_info* info, int32_t n_frames, const int16_t* coef_dev, int64_t coef_stride,
+                              const uint16_t* quant_dev, int64_t quant_stride, uint8_t* scratch_dev, uint8_t* rgb_dev, void* stream) {
     if (!valid_info(info) || !coef_dev || !scratch_dev || !rgb_dev) return jfail(VOSJPEG_ERR_INVALID, "null pointer or bad info");
-    if ((reinterpret_cast<uintptr_t>(coef_dev) & 15) || (reinterpret_cast<uintptr_t>(scratch_dev) & 7))
-        return jfail(VOSJPEG_ERR_INVALID, "coefficients must be 16-byte and scratch 8-byte aligned");
-    const ReconParams rp = make_params(*info);
+    if (n_frames < 1 || n_frames > 65535 || info->height > 65535) return jfail(VOSJPEG_ERR_INVALID, "1 .. 65535 frames (and rows) per launch");
+    if ((reinterpret_cast<uintptr_t>(coef_dev) & 15) || (coef_stride & 7) || (reinterpret_cast<uintptr_t>(scratch_dev) & 7) ||
+        (reinterpret_cast<uintptr_t>(quant_dev) & 1))
+        return jfail(VOSJPEG_ERR_INVALID, "coefficients must be 16-byte aligned (stride a multiple of 8 values), scratch 8-byte aligned");
+    if (n_frames > 1 && coef_stride < info->coef_count) return jfail(VOSJPEG_ERR_INVALID, "coefficient stride shorter than a frame");
+    BatchParams bp;
+    bp.rp = make_params(*info);
+    bp.coef_stride = coef_stride;
+    bp.quant = quant_dev;
+    bp.quant_stride = quant_stride;
+    bp.scratch_stride = (vosjpeg_scratch_bytes(info) + 7) & ~static_cast<int64_t>(7);
     const int64_t n_blocks = info->coef_count / 64;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    vosjpeg_idct<<<static_cast<unsigned>((n_blocks + 127) / 128), 128, 0, st>>>(rp, coef_dev, scratch_dev, n_blocks);
-    vosjpeg_colour<<<dim3((info->width + 255) / 256, info->height), 256, 0, st>>>(rp, scratch_dev, rgb_dev);
+    vosjpeg_idct<<<dim3(static_cast<unsigned>((n_blocks + kIdctBlocksPerCta - 1) / kIdctBlocksPerCta), n_frames), kIdctBlocksPerCta * 8, 0, st>>>(
+        bp, coef_dev, scratch_dev, n_blocks);
+    vosjpeg_colour<<<dim3((info->width + 511) / 512, info->height, n_frames), 128, 0, st>>>(bp, scratch_dev, rgb_dev);
     const cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return jfail(VOSJPEG_ERR_CUDA, "%s", cudaGetErrorString(err));
     return VOSJPEG_OK;
+}
+
+int vosjpeg_reconstruct(const vosjpeg_info* info, const int16_t* coef_dev, uint8_t* scratch_dev, uint8_t* rgb_dev, void* stream) {
+    return vosjpeg_reconstruct_batch(info, 1, coef_dev, info ? info->coef_count : 0, nullptr, 0, scratch_dev, rgb_dev, stream);
 }
 
 int vosjpeg_reconstruct_host(const vosjpeg_info* info, const int16_t* coef, uint8_t* rgb) {

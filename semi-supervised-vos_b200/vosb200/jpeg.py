@@ -41,6 +41,8 @@ EXPORTS = {
     'vosjpeg_entropy_decode': (C.c_int, [C.c_char_p, C.c_int64, C.POINTER(Info), C.c_void_p]),
     'vosjpeg_scratch_bytes': (C.c_int64, [C.POINTER(Info)]),
     'vosjpeg_reconstruct': (C.c_int, [C.POINTER(Info), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'vosjpeg_reconstruct_batch': (C.c_int, [C.POINTER(Info), C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                            C.c_void_p]),
     'vosjpeg_reconstruct_host': (C.c_int, [C.POINTER(Info), C.c_void_p, C.c_void_p]),
 }
 _bound = None
@@ -128,10 +130,32 @@ def unpack_items(items: torch.Tensor, device) -> torch.Tensor:
     if items.dtype != torch.int16 or items.dim() != 2:
         raise ValueError('items: (n, L) int16')
     infos = [Info.from_buffer_copy(items[i, :_HDR_I16].contiguous().numpy().tobytes()[:C.sizeof(Info)]) for i in range(items.shape[0])]
-    dev = items.to(device, non_blocking=True)
-    out = torch.empty((items.shape[0], infos[0].height, infos[0].width, 3), dtype=torch.uint8, device=device)
-    for i, info in enumerate(infos):
-        if (info.height, info.width) != (infos[0].height, infos[0].width) or _HDR_I16 + info.coef_count != items.shape[1]:
+    for info in infos:
+        same = all(list(getattr(info, k)) == list(getattr(infos[0], k)) for k in ('h_samp', 'v_samp', 'blocks_w', 'blocks_h'))
+        if (info.height, info.width, info.n_comp) != (infos[0].height, infos[0].width, infos[0].n_comp) or not same or \
+                _HDR_I16 + info.coef_count != items.shape[1]:
             raise ValueError('items of one batch must share their geometry')
-        reconstruct(info, dev[i, _HDR_I16:], out=out[i])
+    dev = items.to(device, non_blocking=True)
+    if not dev.is_cuda:
+        out = torch.empty((items.shape[0], infos[0].height, infos[0].width, 3), dtype=torch.uint8)
+        for i, inf in enumerate(infos):
+            reconstruct(inf, dev[i, _HDR_I16:], out=out[i])
+        return out
+    return reconstruct_items(infos[0], dev)
+
+
+def reconstruct_items(info: Info, dev: torch.Tensor) -> torch.Tensor:
+    """Device stage for a batch of loader items already on the GPU ((n, L) int16, one geometry = `info`'s): one launch pair; each
+    frame's quantisation tables are read from its own header, which travelled with it."""
+    n = dev.shape[0]
+    out = torch.empty((n, info.height, info.width, 3), dtype=torch.uint8, device=dev.device)
+    quant_off = Info.quant.offset // 2
+    with torch.cuda.device(dev.device):
+        per_frame = (_lib().vosjpeg_scratch_bytes(C.byref(info)) + 7) // 8 * 8
+        scratch = torch.empty(n * per_frame, dtype=torch.uint8, device=dev.device)
+        stream = torch.cuda.current_stream(dev.device)
+        _check(_lib().vosjpeg_reconstruct_batch(C.byref(info), n, dev.data_ptr() + 2 * _HDR_I16, dev.shape[1], dev.data_ptr() + 2 * quant_off,
+                                                dev.shape[1], scratch.data_ptr(), out.data_ptr(), C.c_void_p(stream.cuda_stream)))
+        scratch.record_stream(stream)
+        dev.record_stream(stream)
     return out

@@ -170,7 +170,8 @@ def test_480p_frames_on_the_device_and_through_the_loop_input_stage():
     datas = [encode(picture(480, 854, seed=k, noise=4.0 + 6 * k), quality=q, subsampling=s) for k, (q, s) in enumerate(((90, 2), (75, 1), (95, 0)))]
     for d in datas:
         assert np.array_equal(J.decode(d, device='cuda').cpu().numpy(), pillow(d))
-    same = [encode(picture(480, 854, seed=10 + k, noise=5.0), quality=90) for k in range(4)]
+    # one batch = one launch pair; the frames differ in quality, i.e. in their quantisation tables (read from each item's header)
+    same = [encode(picture(480, 854, seed=10 + k, noise=5.0), quality=q) for k, q in enumerate((90, 60, 75, 95, 90))]
     items = torch.stack([J.pack_item(d) for d in same])
     got = _to_device(items)                                             # what the loops feed the network
     want = normalize_frames(torch.from_numpy(np.stack([pillow(d) for d in same])).cuda(), torch.float32)

@@ -46,7 +46,8 @@ def main():
         ckpt = root / 'ckpt.pth.tar'
         torch.manual_seed(0)
         torch.save({'state_dict': VOSNet('resnet50', pretrained=False).state_dict()}, ckpt)
-        for strategy in ('single', 'single', 'hor-flip', '3-scale'):      # first 'single' warms cuDNN / the page cache up
+        # first 'single' warms cuDNN / the page cache up; `python tools/bench_cli.py single single` runs just those
+        for strategy in (sys.argv[1:] or ('single', 'single', 'hor-flip', '3-scale')):
             save = root / f'out_{strategy}_{time.time_ns()}'
             t0 = time.perf_counter()
             inference_command_impl(9, str(root), str(ckpt), 'resnet50', 1.0, 40, 8.0, 21.0, str(save), 'cuda', strategy,
@@ -54,7 +55,8 @@ def main():
             dt = time.perf_counter() - t0
             n_png = len(list(save.glob('*/*.png')))
             print(json.dumps({'config': 'main.py inference (wall clock, model load and dataset read included)',
-                              'strategy': strategy, 'videos': videos, 'frames': videos * frames, 'pngs_written': n_png,
+                              'strategy': strategy, 'gpu_jpeg': __import__('os').environ.get('VOS_GPU_JPEG', '1') != '0',
+                              'host_cpus': len(__import__('os').sched_getaffinity(0)), 'videos': videos, 'frames': videos * frames, 'pngs_written': n_png,
                               'seconds': round(dt, 3), 'frames_per_s': round(videos * frames / dt, 1)}), flush=True)
 
 
