@@ -14,7 +14,7 @@
 
 #include "../../include/vos_jpeg.h"
 
-namespace {
+namespace vosj {
 
 thread_local char g_err[256] = "";
 int jfail(int code, const char* fmt, ...) {
@@ -559,7 +559,9 @@ __global__ void __launch_bounds__(128) vosjpeg_colour(const __grid_constant__ Ba
     }
 }
 
-}  // namespace
+}  // namespace vosj
+
+using namespace vosj;
 
 extern "C" {
 
