@@ -44,6 +44,13 @@ int vosjpeg_parse(const uint8_t* data, int64_t size, vosjpeg_info* info);
  * host memory) is overwritten completely.  Replaces the entropy-decoding half of Image.convert('RGB') (datasets.py:142). */
 int vosjpeg_entropy_decode(const uint8_t* data, int64_t size, const vosjpeg_info* info, int16_t* coef);
 
+/* Host stage for a batch of files on `n_threads` threads of the library's own (what a DataLoader's worker processes do for the
+ * reference, datasets.py:141-143, without the inter-process copies): file i -> items[i] = [vosjpeg_info, zero-padded to
+ * header_values int16][coefficients], status[i] = VOSJPEG_OK or the error (VOSJPEG_ERR_UNSUPPORTED: decode that file with Pillow;
+ * also returned when header_values + coef_count exceeds item_capacity values). */
+int vosjpeg_decode_files_host(const uint8_t* const* datas, const int64_t* sizes, int32_t n_files, int16_t* const* items, int64_t item_capacity,
+                              int32_t header_values, int32_t n_threads, int32_t* status);
+
 /* Scratch the device stage needs for one frame (the three sample planes). */
 int64_t vosjpeg_scratch_bytes(const vosjpeg_info* info);
 

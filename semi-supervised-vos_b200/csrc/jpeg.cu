@@ -8,9 +8,12 @@
 // HBM-bound byte / integer work: 1.2 MB of coefficients in, 1.2 MB of RGB out per 480p frame; no tensor cores involved.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 #include "../../include/vos_jpeg.h"
 
@@ -652,6 +655,35 @@ int vosjpeg_entropy_decode(const uint8_t* data, int64_t size, const vosjpeg_info
 done:
     delete ps;
     return rc;
+}
+
+int vosjpeg_decode_files_host(const uint8_t* const* datas, const int64_t* sizes, int32_t n_files, int16_t* const* items, int64_t item_capacity,
+                              int32_t header_values, int32_t n_threads, int32_t* status) {
+    if (!datas || !sizes || !items || !status || n_files < 0) return jfail(VOSJPEG_ERR_INVALID, "null pointer");
+    if (header_values < 0 || static_cast<size_t>(header_values) * sizeof(int16_t) < sizeof(vosjpeg_info) || (header_values & 7))
+        return jfail(VOSJPEG_ERR_INVALID, "header: at least sizeof(vosjpeg_info) bytes, a multiple of 8 values");
+    std::atomic<int32_t> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const int32_t i = next.fetch_add(1);
+            if (i >= n_files) return;
+            vosjpeg_info info;
+            int rc = vosjpeg_parse(datas[i], sizes[i], &info);
+            if (rc == VOSJPEG_OK && header_values + info.coef_count > item_capacity) rc = VOSJPEG_ERR_UNSUPPORTED;    // larger than the caller planned for
+            if (rc == VOSJPEG_OK) {
+                memset(items[i], 0, static_cast<size_t>(header_values) * sizeof(int16_t));
+                memcpy(items[i], &info, sizeof(info));
+                rc = vosjpeg_entropy_decode(datas[i], sizes[i], &info, items[i] + header_values);
+            }
+            status[i] = rc;
+        }
+    };
+    const int32_t n_thr = n_threads < 1 ? 1 : (n_threads > n_files ? n_files : n_threads);
+    std::vector<std::thread> pool;
+    for (int32_t t = 1; t < n_thr; ++t) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    return VOSJPEG_OK;
 }
 
 int64_t vosjpeg_scratch_bytes(const vosjpeg_info* info) {

@@ -96,6 +96,9 @@ def inference_command_impl(ref_num, data, resume, model, temperature, frame_rang
     # the reference decodes with one worker (inference.py:75-78); JPEG decode is the slowest stage once propagation runs on
     # the GPU, so it is spread over workers here (same PIL decode, same order: shuffle=False)
     cpus = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    # (An in-process loader on the library's own threads -- vosjpeg_decode_files_host for 8 files at a time, one group ahead -- was
+    # measured against the worker processes: 540-598 vs 684-719 frames/s on 16 host threads, 450-475 vs 519-535 on 4: the producer
+    # thread shares the interpreter with the launch loop.  Workers stay.)
     loader = torch.utils.data.DataLoader(dataset, batch_size=1, shuffle=False, num_workers=max(1, min(12, cpus - 4, cpus)) if cpus > 8 else min(8, cpus),
                                          pin_memory=True, prefetch_factor=4, persistent_workers=False)
     annotation_dir = Path(data) / 'Annotations/480p'

@@ -116,3 +116,4 @@ class InferenceDataset(datasets.ImageFolder):
 
     def __len__(self):
         return len(self.imgs)
+

@@ -39,6 +39,8 @@ EXPORTS = {
     'vosjpeg_last_error': (C.c_char_p, []),
     'vosjpeg_parse': (C.c_int, [C.c_char_p, C.c_int64, C.POINTER(Info)]),
     'vosjpeg_entropy_decode': (C.c_int, [C.c_char_p, C.c_int64, C.POINTER(Info), C.c_void_p]),
+    'vosjpeg_decode_files_host': (C.c_int, [C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_void_p), C.c_int64, C.c_int32,
+                                            C.c_int32, C.POINTER(C.c_int32)]),
     'vosjpeg_scratch_bytes': (C.c_int64, [C.POINTER(Info)]),
     'vosjpeg_reconstruct': (C.c_int, [C.POINTER(Info), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'vosjpeg_reconstruct_batch': (C.c_int, [C.POINTER(Info), C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
@@ -159,3 +161,28 @@ def reconstruct_items(info: Info, dev: torch.Tensor) -> torch.Tensor:
         scratch.record_stream(stream)
         dev.record_stream(stream)
     return out
+
+
+def pack_items_threaded(datas, capacity: int, threads: int, pinned: bool = False):
+    """Host half of the decode for a batch of files on the library's own threads (GIL released for the whole batch): returns
+    (buffer (n, capacity) int16, status list).  Row i holds file i's loader item in its first _HDR_I16 + coef_count values when
+    status[i] == 0; status ERR_UNSUPPORTED: decode that file with Pillow."""
+    n = len(datas)
+    buf = torch.empty((n, capacity), dtype=torch.int16, pin_memory=pinned)
+    arr = (C.c_char_p * n)(*datas)
+    sizes = (C.c_int64 * n)(*[len(d) for d in datas])
+    ptrs = (C.c_void_p * n)(*[buf.data_ptr() + 2 * capacity * i for i in range(n)])
+    status = (C.c_int32 * n)()
+    _check(_lib().vosjpeg_decode_files_host(arr, sizes, n, ptrs, capacity, _HDR_I16, threads, status))
+    return buf, list(status)
+
+
+def item_length(data: bytes) -> int:
+    """Values a loader item of this file takes (header + coefficients)."""
+    return _HDR_I16 + parse(data).coef_count
+
+
+def item_values(item: torch.Tensor) -> int:
+    """Length (in int16 values) of the loader item that starts at item[0] (its header says how many coefficients follow)."""
+    info = Info.from_buffer_copy(item[:_HDR_I16].contiguous().numpy().tobytes()[:C.sizeof(Info)])
+    return _HDR_I16 + info.coef_count

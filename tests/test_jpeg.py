@@ -176,3 +176,19 @@ def test_480p_frames_on_the_device_and_through_the_loop_input_stage():
     got = _to_device(items)                                             # what the loops feed the network
     want = normalize_frames(torch.from_numpy(np.stack([pillow(d) for d in same])).cuda(), torch.float32)
     assert got.shape == want.shape and torch.equal(got, want)
+
+
+
+def test_batch_of_files_on_the_librarys_threads():
+    """vosjpeg_decode_files_host: the host stage for a batch of files on several threads == one pack_item per file; a flavour
+    outside the path and a frame larger than planned for are reported per file, the others are unaffected."""
+    datas = [encode(picture(72, 104, seed=k), quality=80 + k) for k in range(9)]
+    datas[3] = encode(picture(72, 104, seed=3), quality=85, progressive=True)
+    datas[6] = encode(picture(144, 208, seed=6), quality=85)
+    capacity = J.item_length(datas[0])
+    for threads in (1, 3, 16):
+        buf, status = J.pack_items_threaded(datas, capacity, threads)
+        assert status == [0, 0, 0, J.ERR_UNSUPPORTED, 0, 0, J.ERR_UNSUPPORTED, 0, 0]
+        for i, st in enumerate(status):
+            if st == 0:
+                assert J.item_values(buf[i]) == capacity and torch.equal(buf[i], J.pack_item(datas[i])), (threads, i)
