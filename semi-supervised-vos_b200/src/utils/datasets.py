@@ -116,4 +116,3 @@ class InferenceDataset(datasets.ImageFolder):
 
     def __len__(self):
         return len(self.imgs)
-
