@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <new>
 #include <thread>
 #include <vector>
 
@@ -572,7 +573,8 @@ const char* vosjpeg_last_error(void) { return g_err; }
 
 int vosjpeg_parse(const uint8_t* data, int64_t size, vosjpeg_info* info) {
     if (!data || !info) return jfail(VOSJPEG_ERR_INVALID, "null pointer");
-    Parsed* ps = new Parsed();
+    Parsed* ps = new (std::nothrow) Parsed();
+    if (!ps) return jfail(VOSJPEG_ERR_INVALID, "out of memory");
     const int rc = parse_impl(data, size, *ps, false);
     if (rc == VOSJPEG_OK) *info = ps->info;
     delete ps;
@@ -581,7 +583,8 @@ int vosjpeg_parse(const uint8_t* data, int64_t size, vosjpeg_info* info) {
 
 int vosjpeg_entropy_decode(const uint8_t* data, int64_t size, const vosjpeg_info* info, int16_t* coef) {
     if (!data || !info || !coef) return jfail(VOSJPEG_ERR_INVALID, "null pointer");
-    Parsed* ps = new Parsed();
+    Parsed* ps = new (std::nothrow) Parsed();
+    if (!ps) return jfail(VOSJPEG_ERR_INVALID, "out of memory");
     int rc = parse_impl(data, size, *ps, true);
     if (rc == VOSJPEG_OK && memcmp(&ps->info, info, sizeof(*info)) != 0) rc = jfail(VOSJPEG_ERR_INVALID, "info does not belong to this stream");
     if (rc != VOSJPEG_OK) {
@@ -680,7 +683,11 @@ int vosjpeg_decode_files_host(const uint8_t* const* datas, const int64_t* sizes,
     };
     const int32_t n_thr = n_threads < 1 ? 1 : (n_threads > n_files ? n_files : n_threads);
     std::vector<std::thread> pool;
-    for (int32_t t = 1; t < n_thr; ++t) pool.emplace_back(work);
+    try {
+        for (int32_t t = 1; t < n_thr; ++t) pool.emplace_back(work);
+    } catch (...) {
+        // no more threads to be had: the ones that started and this one share the files
+    }
     work();
     for (auto& th : pool) th.join();
     return VOSJPEG_OK;
@@ -725,7 +732,8 @@ int vosjpeg_reconstruct_host(const vosjpeg_info* info, const int16_t* coef, uint
     if (!valid_info(info) || !coef || !rgb) return jfail(VOSJPEG_ERR_INVALID, "null pointer or bad info");
     const ReconParams rp = make_params(*info);
     const int64_t bytes = vosjpeg_scratch_bytes(info);
-    uint8_t* planes = new uint8_t[bytes];
+    uint8_t* planes = new (std::nothrow) uint8_t[bytes];
+    if (!planes) return jfail(VOSJPEG_ERR_INVALID, "out of memory");
     for (int c = 0; c < info->n_comp; ++c)
         for (int by = 0; by < info->blocks_h[c]; ++by)
             for (int bx = 0; bx < info->blocks_w[c]; ++bx)
