@@ -43,6 +43,7 @@ class Header:
         self.hmax = self.vmax = 1
         self.mcus_x = self.mcus_y = 0
         self.adobe_transform = None
+        self.jfif = False
 
 
 def parse(data: bytes) -> Header:
@@ -96,6 +97,8 @@ def parse(data: bytes) -> Header:
                 j += 17 + n
         elif m == 0xDD:
             h.restart = (seg[0] << 8) | seg[1]
+        elif m == 0xE0 and seg[:5] == b'JFIF\0':
+            h.jfif = True
         elif m == 0xEE and seg[:5] == b'Adobe':
             h.adobe_transform = seg[11]
         elif m == 0xDA:                              # SOS
@@ -116,6 +119,8 @@ def parse(data: bytes) -> Header:
         raise Unsupported('%d components' % len(h.comps))
     if len(h.comps) == 3 and h.adobe_transform not in (None, 1):
         raise Unsupported('Adobe colour transform %r' % h.adobe_transform)
+    if len(h.comps) == 3 and not h.jfif and h.adobe_transform is None and [c.cid for c in h.comps] == [82, 71, 66]:
+        raise Unsupported("components named 'R', 'G', 'B' without a JFIF / Adobe marker: libjpeg takes them as RGB data (jdapimin.c)")
     h.hmax, h.vmax = max(c.h for c in h.comps), max(c.v for c in h.comps)
     if len(h.comps) == 1:                            # a single-component scan is never interleaved: MCU = one block
         h.comps[0].h = h.comps[0].v = h.hmax = h.vmax = 1

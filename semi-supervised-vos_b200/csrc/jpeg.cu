@@ -170,7 +170,7 @@ int parse_impl(const uint8_t* d, int64_t size, Parsed& ps, bool want_tables) {
     bool qt_present[4] = {false, false, false, false};
     int comp_id[3] = {0, 0, 0}, comp_tq[3] = {0, 0, 0};
     int adobe_transform = -1;
-    bool have_sof = false;
+    bool have_sof = false, saw_jfif = false;
     int64_t i = 2;
     for (;;) {
         if (i + 4 > size) return jfail(VOSJPEG_ERR_INVALID, "truncated before the scan");
@@ -230,6 +230,8 @@ int parse_impl(const uint8_t* d, int64_t size, Parsed& ps, bool want_tables) {
         } else if (m == 0xDD) {
             if (n < 2) return jfail(VOSJPEG_ERR_INVALID, "bad restart interval");
             info.restart_interval = (s[0] << 8) | s[1];
+        } else if (m == 0xE0 && n >= 5 && memcmp(s, "JFIF", 5) == 0) {
+            saw_jfif = true;
         } else if (m == 0xEE && n >= 12 && memcmp(s, "Adobe", 5) == 0) {
             adobe_transform = s[11];
         } else if (m == 0xDA) {
@@ -251,6 +253,10 @@ int parse_impl(const uint8_t* d, int64_t size, Parsed& ps, bool want_tables) {
     }
     if (info.n_comp == 3 && adobe_transform != -1 && adobe_transform != 1)
         return jfail(VOSJPEG_ERR_UNSUPPORTED, "Adobe colour transform %d (RGB / CMYK data)", adobe_transform);
+    // libjpeg's colour-space guess (jdapimin.c default_decompress_parms): without a JFIF or Adobe marker, components named
+    // 'R', 'G', 'B' are taken as RGB data and not converted
+    if (info.n_comp == 3 && !saw_jfif && adobe_transform == -1 && comp_id[0] == 'R' && comp_id[1] == 'G' && comp_id[2] == 'B')
+        return jfail(VOSJPEG_ERR_UNSUPPORTED, "components named R, G, B without a JFIF / Adobe marker (RGB data)");
     if (info.n_comp == 1) info.h_samp[0] = info.v_samp[0] = 1;    // a one-component scan is never interleaved: MCU = one block
     int hmax = 1, vmax = 1;
     for (int c = 0; c < info.n_comp; ++c) {

@@ -106,6 +106,35 @@ def test_flavours_outside_the_path_are_refused_not_decoded():
         J.parse(encode(a)[:100])
 
 
+def _without_jfif(data, ids=None):
+    """The stream without its APP0 JFIF segment, optionally with the component identifiers of SOF0 / SOS replaced."""
+    assert data[2:4] == b'\xff\xe0'
+    out = bytearray(data[:2] + data[4 + ((data[4] << 8) | data[5]):])
+    if ids is not None:
+        sof = out.index(b'\xff\xc0')
+        sos = out.index(b'\xff\xda')
+        for c, cid in enumerate(ids):
+            out[sof + 10 + 3 * c] = cid
+            out[sos + 5 + 2 * c] = cid
+    return bytes(out)
+
+
+def test_colour_space_guess_follows_libjpeg():
+    """jdapimin.c: no JFIF / Adobe marker -> components 1, 2, 3 (or anything unknown) are YCbCr, but 'R', 'G', 'B' are RGB data
+    that Pillow returns unconverted: that file is refused (the loader keeps Pillow for it), the others decode to Pillow's bytes."""
+    data = encode(picture(40, 56, seed=2), quality=90, subsampling=0)
+    plain = _without_jfif(data)
+    assert np.array_equal(J.decode(plain).numpy(), pillow(plain)) and np.array_equal(O.decode(plain), pillow(plain))
+    odd = _without_jfif(data, ids=(7, 8, 9))
+    assert np.array_equal(J.decode(odd).numpy(), pillow(odd))
+    rgb = _without_jfif(data, ids=(ord('R'), ord('G'), ord('B')))
+    assert not np.array_equal(pillow(rgb), pillow(plain))           # Pillow really treats it differently
+    with pytest.raises(J.Unsupported):
+        J.parse(rgb)
+    with pytest.raises(O.Unsupported):
+        O.parse(rgb)
+
+
 def test_damaged_streams_never_crash():
     """Truncations and flipped bytes: an error or some picture, never a fault (bounds are the library's business)."""
     rs = np.random.RandomState(5)
