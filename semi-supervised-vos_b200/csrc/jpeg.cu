@@ -271,6 +271,7 @@ int parse_impl(const uint8_t* d, int64_t size, Parsed& ps, bool want_tables) {
         const bool ok = hmax % info.h_samp[c] == 0 && vmax % info.v_samp[c] == 0 &&
                         ((fh == 1 && fv == 1) || (fh == 2 && fv == 1) || (fh == 2 && fv == 2));
         if (!ok) return jfail(VOSJPEG_ERR_UNSUPPORTED, "sampling factors %dx%d of %dx%d", info.h_samp[c], info.v_samp[c], hmax, vmax);
+        if (c == 0 && (fh != 1 || fv != 1)) return jfail(VOSJPEG_ERR_UNSUPPORTED, "first component below full resolution");
         if (!qt_present[comp_tq[c]]) return jfail(VOSJPEG_ERR_INVALID, "missing quantisation table %d", comp_tq[c]);
         memcpy(info.quant[c], qt[comp_tq[c]], sizeof(qt[0]));
     }

@@ -100,6 +100,11 @@ def test_flavours_outside_the_path_are_refused_not_decoded():
             data = data.getvalue()
         with pytest.raises(J.Unsupported):
             J.parse(data)
+    swapped = bytearray(encode(a, quality=85, subsampling=2))       # luma 1x1 under 2x2 chroma: no encoder writes it, the device
+    sof = swapped.index(b'\xff\xc0')                                 # stage reads luma at full resolution -> refused
+    swapped[sof + 11], swapped[sof + 14], swapped[sof + 17] = 0x11, 0x22, 0x22
+    with pytest.raises(J.Unsupported):
+        J.parse(bytes(swapped))
     with pytest.raises(J.JpegError):
         J.parse(b'not a jpeg at all')
     with pytest.raises(J.JpegError):
