@@ -42,6 +42,8 @@ constexpr int kLook = 11;
 struct HuffTable {
     bool present = false;
     uint16_t look[1 << kLook];      // (code length << 8) | symbol; 0: code longer than kLook bits
+    int16_t fast_ac[1 << kLook];    // AC tables: (value << 8) | (run << 4) | (code length + value bits) when both fit the look-ahead
+                                    // window and the value fits 8 bits; 0 otherwise.  Most AC coefficients of a photograph do.
     int32_t maxcode[18];            // largest code of each length (-1: none); [17] = sentinel
     int32_t valoff[17];             // symbol index of the first code of each length minus that code
     uint8_t symbols[256];
@@ -69,6 +71,14 @@ bool build_table(const uint8_t* counts, const uint8_t* symbols, int n_sym, HuffT
     }
     t.maxcode[17] = 0x7fffffff;
     t.present = true;
+    for (int i = 0; i < (1 << kLook); ++i) {
+        const uint32_t e = t.look[i];
+        const int len = static_cast<int>(e >> 8), run = static_cast<int>((e >> 4) & 15u), mag = static_cast<int>(e & 15u);
+        if (e == 0 || mag == 0 || len + mag > kLook) continue;
+        int v = ((i << len) & ((1 << kLook) - 1)) >> (kLook - mag);          // the value bits that follow the code
+        if (v < (1 << (mag - 1))) v += 1 - (1 << mag);                         // T.81 F.2.2.1 EXTEND
+        if (v >= -128 && v <= 127) t.fast_ac[i] = static_cast<int16_t>(v * 256 + run * 16 + len + mag);
+    }
     return k == n_sym;
 }
 
@@ -637,6 +647,18 @@ int vosjpeg_entropy_decode(const uint8_t* data, int64_t size, const vosjpeg_info
                         blk[0] = static_cast<int16_t>(pred[c]);
                         for (int k = 1; k < 64;) {
                             br.ensure();
+                            const int fast = act.fast_ac[br.peek(kLook)];
+                            if (fast) {                                     // code and value in one look-up
+                                k += (fast >> 4) & 15;
+                                if (k > 63) {
+                                    rc = jfail(VOSJPEG_ERR_INVALID, "corrupt entropy-coded data");
+                                    goto done;
+                                }
+                                br.skip(fast & 15);
+                                blk[kZigzag[k]] = static_cast<int16_t>(fast >> 8);
+                                ++k;
+                                continue;
+                            }
                             const int rs = decode_symbol(br, act);
                             if (rs < 0) {
                                 rc = jfail(VOSJPEG_ERR_INVALID, "corrupt entropy-coded data");
