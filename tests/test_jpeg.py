@@ -226,3 +226,21 @@ def test_batch_of_files_on_the_librarys_threads():
         for i, st in enumerate(status):
             if st == 0:
                 assert J.item_values(buf[i]) == capacity and torch.equal(buf[i], J.pack_item(datas[i])), (threads, i)
+
+
+def test_worker_processes_ship_coefficients(tmp_path):
+    """The command's loader: DataLoader worker processes run the host stage (the library is loaded in the workers, no CUDA call)
+    and the items that come back decode to Pillow's frames, in order."""
+    from src.utils.datasets import InferenceDataset
+    root = tmp_path / 'JPEGImages'
+    (root / 'v').mkdir(parents=True)
+    for t in range(10):
+        (root / 'v' / f'{t:05d}.jpg').write_bytes(encode(picture(96, 128, seed=t), quality=90, subsampling=t % 3))
+    ds = InferenceDataset(str(root), disable=True, raw='coef')
+    loader = torch.utils.data.DataLoader(ds, batch_size=1, shuffle=False, num_workers=2, prefetch_factor=2)
+    seen = 0
+    for i, (item, (video,)) in enumerate(loader):
+        assert video == 'v' and item.dtype == torch.int16
+        assert np.array_equal(J.unpack_items(item, 'cpu')[0].numpy(), pillow((root / 'v' / f'{i:05d}.jpg').read_bytes())), i
+        seen += 1
+    assert seen == 10
