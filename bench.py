@@ -17,7 +17,7 @@ at the end of the run.  --workload ytvos: configs[4]; --workload uniform: the we
           pinned host memory -> H2D -> VOSNet on cuDNN -> propagation -> uint8 masks -> D2H, per step.
   roofline     : the fused affinity kernel against the measured bf16 tensor peak (algorithmic FLOPs
                  2*P*(R*P)*K per launch, CUDA events around every launch of the timed region).
-  split3, roofline_topk : (N = 1) sub-records of the same run on a sample of the workload: fp32 embeddings
+  split3, roofline_topk, jpeg_front_end : (N = 1) sub-records of the same run on a sample of the workload: fp32 embeddings
                  (bf16 hi+lo, three passes) and the top-k extension (k = 5, 20, 50).
   cpu_baseline : the reference's CPU path on this box's host cores, bounded sample.
 --impl reference times that CPU path end to end: the reference's own code when its sources are
@@ -302,6 +302,61 @@ def traffic_bytes(precision):
         return None
 
 
+def jpeg_sub_record(dev, H, W, peak_hbm):
+    """Row N3 in the driver's line: the loader's JPEG decode split into the host Huffman stage (next to Pillow's full decode, one
+    core each) and the device stage (vosjpeg_idct + vosjpeg_colour, 32 frames per launch pair, CUDA events, L2 flushed) against the
+    HBM roofline.  Never fails the bench: an exception is reported in the record."""
+    try:
+        import io
+
+        import numpy as np
+        import torch
+        from PIL import Image
+        from vosb200 import jpeg as J
+        rs = np.random.RandomState(0)
+        base = np.asarray(Image.fromarray(rs.randint(0, 256, (H // 32 + 1, W // 32 + 1, 3)).astype(np.uint8)).resize((W, H), Image.BILINEAR))
+        buf = io.BytesIO()
+        Image.fromarray(base).save(buf, format='JPEG', quality=90)
+        data = buf.getvalue()
+        want = np.asarray(Image.open(io.BytesIO(data)).convert('RGB'))
+        info = J.parse(data)
+        coef = J.entropy_decode(data, info)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            J.entropy_decode(data, info, out=coef)
+        host_ms = (time.perf_counter() - t0) / 20 * 1e3
+        t0 = time.perf_counter()
+        for _ in range(20):
+            np.asarray(Image.open(io.BytesIO(data)).convert('RGB'))
+        pil_ms = (time.perf_counter() - t0) / 20 * 1e3
+        n = 32
+        items = torch.stack([J.pack_item(data)] * n).to(dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        ms = []
+        for it in range(12):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            frames = J.reconstruct_items(info, items)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            if it >= 2:
+                ms.append(e0.elapsed_time(e1))
+        us = sorted(ms)[len(ms) // 2] * 1e3 / n
+        planes = sum(info.blocks_w[c] * info.blocks_h[c] * 64 for c in range(info.n_comp))
+        alg = info.coef_count * 2 + 2 * planes + H * W * 3
+        gbs = alg / us / 1e3
+        return {'frame': f'{H}x{W} JPEG, quality 90, 4:2:0, {len(data) / 1e3:.0f} KB (synthetic)',
+                'identical_to_pillow': bool(np.array_equal(frames[0].cpu().numpy(), want) and np.array_equal(frames[n - 1].cpu().numpy(), want)),
+                'host_huffman_ms': host_ms, 'pillow_full_decode_ms': pil_ms, 'host_cores': 1,
+                'device_stage_us_per_frame': us, 'frames_per_launch_pair': n, 'algorithmic_bytes_per_frame': int(alg),
+                'roofline': {'bound': 'hbm', 'kernel': 'vosjpeg_idct + vosjpeg_colour', 'achieved': gbs, 'peak': peak_hbm, 'unit': 'GB/s',
+                             'frac': gbs / peak_hbm if peak_hbm else None, 'traffic': None},
+                'l2': 'flushed between launches (256 MB written)'}
+    except Exception as e:      # noqa: BLE001 -- a side record must not cost the line
+        return {'error': f'{type(e).__name__}: {e}'}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from vosb200 import PropagationEngine, shard, synthetic
@@ -462,6 +517,8 @@ def run_ours(args, rank, world, local_rank):
                                 'sample': sample_txt, 'full_softmax_value_same_sample': sample_frames_n / (ms_ / 1e3), 'k': topk_rec,
                                 'note': 'achieved = algorithmic FLOPs 2*P*N*K of the frame (counted ONCE; the two scans issue 1 + 1/step of them) '
                                         '/ device time of scan 1 + threshold + scan 2; value = frames/s of the whole top-k propagation stage'}
+
+        sub['jpeg_front_end'] = jpeg_sub_record(dev, H, W, peak_hbm)
 
     # ---------------- e2e through the public API
     e2e = None
