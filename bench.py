@@ -17,8 +17,10 @@ at the end of the run.  --workload ytvos: configs[4]; --workload uniform: the we
           pinned host memory -> H2D -> VOSNet on cuDNN -> propagation -> uint8 masks -> D2H, per step.
   roofline     : the fused affinity kernel against the measured bf16 tensor peak (algorithmic FLOPs
                  2*P*(R*P)*K per launch, CUDA events around every launch of the timed region).
-  split3, roofline_topk, jpeg_front_end : (N = 1) sub-records of the same run on a sample of the workload: fp32 embeddings
+  split3, roofline_topk : (N = 1) sub-records of the same run on a sample of the workload: fp32 embeddings
                  (bf16 hi+lo, three passes) and the top-k extension (k = 5, 20, 50).
+  jpeg_front_end : (N = 1) the loader's JPEG decode (include/vos_jpeg.h): host Huffman stage next to Pillow's decode,
+                 device stage per frame against the HBM peak, pixels compared with Pillow's in the run.
   cpu_baseline : the reference's CPU path on this box's host cores, bounded sample.
 --impl reference times that CPU path end to end: the reference's own code when its sources are
 importable (build container), else the oracle port (the reference is pure Python/torch and does not
